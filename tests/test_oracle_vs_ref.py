@@ -1,0 +1,75 @@
+"""Pins the plain-C oracle against the UNMODIFIED reference compiled into oracle/_ref (skipped when
+that build is absent).  Bit-exact, stage by stage and end to end, on real and synthetic inputs
+including the edge cases the domain has: gray input, tiny images, large flows leaving the image,
+identical frames, non-default parameters, out-of-range ratio."""
+import numpy as np
+import pytest
+
+from conftest import load_frame, synthetic_pair
+
+
+def eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.parametrize("shape,c", [((40, 56), 3), ((33, 47), 1), ((21, 64), 3), ((64, 23), 1)])
+def test_stages_bit_exact(oracle_mod, ref_serial, shape, c):
+    o, r = oracle_mod, ref_serial
+    h, w = shape
+    im1, im2 = synthetic_pair(h, w, c, seed=h * w)
+    rng = np.random.default_rng(1)
+    u = rng.normal(size=shape) * 3
+    v = rng.normal(size=shape) * 3
+    u[0, :] = -5; v[-1, :] = 7          # force out-of-image samples
+    wt = rng.random(shape) + 0.05
+    for lv, (a, b) in enumerate(zip(r.pyramid(im1, ratio=0.75, levels=4), o.pyramid(im1, 0.75, 4))):
+        assert eq(a, b), "pyramid level %d" % lv
+    f1r, f1o = r.im2feature(im1), o.im2feature(im1)
+    assert eq(f1r, f1o)
+    f2 = o.im2feature(im2)
+    for a, b in zip(r.getdxs(f1o, f2), o.getdxs(f1o, f2)):
+        assert eq(a, b)
+    assert eq(r.warpfl(f1o, f2, u, v), o.warpfl(f1o, f2, u, v))
+    assert eq(r.laplacian(u, wt), o.laplacian(u, wt))
+    assert eq(r.resize_to(u, int(h / 0.75), int(w / 0.75), 1 / 0.75), o.resize_to(u, int(h / 0.75), int(w / 0.75), 1 / 0.75))
+    assert eq(r.gaussian(im1, 4 / 3.0, 3), o.gaussian(im1, 4 / 3.0, 3))
+    assert eq(r.bicubic(im1, im2, u, v), o.bicubic_warp(im1, im2, u, v))
+    z = np.zeros(shape)
+    for a, b in zip(r.smoothflow_sor(f1o, f2, f2, z, z, 0.012, 2, 2, 7, c),
+                    o.smoothflow_sor(f1o, f2, f2, z, z, 0.012, 2, 2, 7)):
+        assert eq(a, b)
+
+
+def test_full_real_pair_fork_and_upstream_shapes(oracle_mod, ref_serial):
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    _, rx, ry, rw = ref_serial.coarse2fine_flow_levels(a, b, 8)
+    ox, oy, ow = oracle_mod.coarse2fine_flow(a, b, levels=8)
+    assert eq(rx, ox) and eq(ry, oy) and eq(rw, ow)
+    rx, ry, rw = ref_serial.coarse2fine_flow(a, b, 0.02, 0.6, 40, 4, 2, 15, 0)
+    ox, oy, ow = oracle_mod.coarse2fine_flow(a, b, 0.02, 0.6, 40, 4, 2, 15, 0)
+    assert eq(rx, ox) and eq(ry, oy) and eq(rw, ow)
+
+
+@pytest.mark.parametrize("case", ["identical", "gray_coltype1", "rgb_coltype1", "bad_ratio", "one_level"])
+def test_full_edge_cases(oracle_mod, ref_serial, case):
+    im1, im2 = synthetic_pair(48, 72, 3, seed=5, shift=(2.25, 1.5))
+    kw = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuter=3, nInner=1, nSOR=10, colType=0)
+    if case == "identical":
+        im2 = im1.copy()
+    elif case == "gray_coltype1":
+        im1, im2 = im1[..., :1].copy(), im2[..., :1].copy(); kw["colType"] = 1
+    elif case == "rgb_coltype1":
+        kw["colType"] = 1                    # 3-channel image flagged GRAY: swapped luma at level 0
+    elif case == "bad_ratio":
+        kw["ratio"] = 0.3                    # pyramid silently uses 0.75, flow still scaled by 1/0.3
+    elif case == "one_level":
+        kw["minWidth"] = 60                  # log(60/72)/log(.75) -> 0 levels; use 55 -> 0? keep >=1
+        kw["minWidth"] = 50
+    args = (kw["alpha"], kw["ratio"], kw["minWidth"], kw["nOuter"], kw["nInner"], kw["nSOR"], kw["colType"])
+    if oracle_mod.levels_from_min_width(72, kw["ratio"], kw["minWidth"]) < 1:
+        pytest.skip("no levels")
+    rx, ry, rw = ref_serial.coarse2fine_flow(im1, im2, *args)
+    ox, oy, ow = oracle_mod.coarse2fine_flow(im1, im2, *args)
+    assert eq(rx, ox) and eq(ry, oy) and eq(rw, ow)
+    if case == "identical":
+        assert np.abs(ox).max() == 0 and np.abs(oy).max() == 0
