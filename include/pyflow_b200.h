@@ -1,0 +1,155 @@
+/* pyflow_b200 -- C ABI of the B200-native coarse-to-fine variational optical-flow solver.
+ *
+ * This is the drop-in boundary for the hot path of ElijahHyndman/PAPTeam_OpticalFlow: every
+ * function here replaces (or is a finer-grained view of) one reference interface, cited per
+ * entry as <tree>/<file>:<lines> with S/ = Code/Serial/src, P/ = Code/Parallel/src,
+ * Par/ = Code/Parallel.  Plain pointers and sizes only; all image arguments are HOST pointers to
+ * row-major HWC interleaved float64, exactly the buffers the reference's wrapper receives from
+ * numpy (P/Coarse2FineFlowWrapper.cpp:14-51).  The library copies in and out and retains nothing.
+ *
+ * Every function returns 0 on success or a negative PF_E* code; pf_last_error() describes the
+ * failure of the calling thread.  There is NO CPU fallback: without a usable CUDA device every
+ * compute entry point fails with PF_ENODEVICE.
+ */
+#ifndef PYFLOW_B200_H
+#define PYFLOW_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define PF_OK            0
+#define PF_EINVAL       -1   /* bad argument (NULL pointer, non-positive size, unknown mode ...) */
+#define PF_ENODEVICE    -2   /* no CUDA device / device index out of range */
+#define PF_ECUDA        -3   /* a CUDA runtime call or kernel failed (message has the details) */
+#define PF_ENOMEM       -4   /* host or device allocation failed */
+#define PF_EUNSUPPORTED -5   /* valid request this build does not implement */
+
+/* ---- solver modes (north_star: two required modes, plus the two cross combinations that the
+ *      tests use to separate ordering error from rounding error) ---------------------------- */
+#define PF_MODE_FP64_WAVEFRONT 0 /* FP64, lexicographic Gauss-Seidel as a pipelined anti-diagonal
+                                    wavefront: matches the reference to <=1e-6 (bit-level in practice) */
+#define PF_MODE_FP32_REDBLACK  1 /* FP32, red-black SOR with fused sweeps: the fast mode */
+#define PF_MODE_FP64_REDBLACK  2 /* FP64 arithmetic, red-black ordering */
+#define PF_MODE_FP32_WAVEFRONT 3 /* FP32 arithmetic, lexicographic ordering */
+
+/* ---- timing report: the reference's timing-map keys (S/OpticalFlow.cpp:850-860), in
+ *      milliseconds of GPU time from CUDA events, plus the transfer legs ---------------------- */
+enum {
+    PF_T_TOTAL = 0,        /* "Total C++ Execution": H2D + solve + D2H                      */
+    PF_T_CONSTRUCTION,     /* "Construction": both Gaussian pyramids                         */
+    PF_T_ALLOCATION,       /* "Allocation": im2feature, flow upsampling, per-level warp      */
+    PF_T_PHASE1_GENERATE,  /* "Phase1_Generate": getDxs                                      */
+    PF_T_PHASE2_DERIVS,    /* "Phase2_Derivatives": flow derivatives / phi                   */
+    PF_T_PHASE3_PSI,       /* "Phase3_PsiData" (fused into PHASE4 on the GPU; reported 0)    */
+    PF_T_PHASE4_SYSTEM,    /* "Phase4_LinearSystem": psi, collapsed products, Laplacian, rhs */
+    PF_T_PHASE5_SOR,       /* "Phase5_SOR": the SOR sweeps                                   */
+    PF_T_PHASE6_UPDATE,    /* "Phase6_Update": u+=du, warp, noise estimate                   */
+    PF_T_POST,             /* "PostProcessing": bicubic warp + clamp                         */
+    PF_T_H2D,              /* host->device copy of the two frames                            */
+    PF_T_D2H,              /* device->host copy of vx, vy, warpI2                            */
+    PF_T_SOLVE,            /* device-only solve (no transfers)                               */
+    PF_NUM_TIMINGS = 16
+};
+
+typedef struct pf_plan pf_plan;
+
+/* ---- library / device ---------------------------------------------------------------------- */
+const char* pf_last_error(void);
+const char* pf_version(void);
+int  pf_device_count(void);                       /* number of CUDA devices, 0 if none */
+void* pf_host_alloc(size_t bytes);                /* pinned host memory (NULL on failure) */
+void  pf_host_free(void* p);
+
+/* ---- pyramid geometry: host-only double arithmetic, usable without a GPU --------------------
+ * S/GaussianPyramid.cpp:50-53 (level count from minWidth) and :89-106 + S/Image.h:755-756
+ * (level sizes by double->int truncation). */
+int pf_pyramid_levels(int width, double ratio, int minWidth);
+int pf_level_geometry(int w, int h, double ratio, int levels, int* widths, int* heights);
+
+/* ---- one-shot solves --------------------------------------------------------------------------
+ * Upstream pyflow call shape named by north_star (parameter list survives at Par/pyflow.pyx:36-41;
+ * declared at S/OpticalFlow.h:49-50).  timings may be NULL or point to PF_NUM_TIMINGS doubles. */
+int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im1,
+                        const double* im2, double alpha, double ratio, int minWidth,
+                        int nOuterFPIterations, int nInnerFPIterations, int nSORIterations,
+                        int colType, int h, int w, int c, int mode, int device, double* timings);
+
+/* The fork's call shape: replaces Coarse2FineFlowWrapper (P/Coarse2FineFlowWrapper.h:12-15,
+ * P/Coarse2FineFlowWrapper.cpp:14-51) with its hard-coded alpha=0.012 ratio=0.75 7/1/30
+ * (S/OpticalFlow.cpp:747-751) and colType=0.  nCores is accepted and ignored. */
+int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const double* im1,
+                               const double* im2, int pyramidLevels, int nCores, int h, int w,
+                               int c, int mode, int device, double* timings);
+
+/* ---- plans: device arena + captured CUDA graph for one (h, w, c, parameters, mode, device) ---
+ * levels > 0 selects the fork's explicit level count, otherwise minWidth decides. */
+int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                   int levels, int nOuterFPIterations, int nInnerFPIterations, int nSORIterations,
+                   int colType, int mode, int device);
+int pf_plan_destroy(pf_plan* plan);
+int pf_plan_levels(const pf_plan* plan);
+/* H2D + solve + D2H with host buffers (pageable or pinned). */
+int pf_plan_execute(pf_plan* plan, double* vx, double* vy, double* warpI2, const double* im1,
+                    const double* im2, double* timings);
+/* The same three legs separately, for resident-input measurement. */
+int pf_plan_upload(pf_plan* plan, const double* im1, const double* im2);
+int pf_plan_solve(pf_plan* plan, int repeats, double* ms_total);
+int pf_plan_download(pf_plan* plan, double* vx, double* vy, double* warpI2);
+/* One eager (un-graphed) solve with CUDA events around every phase; fills PF_NUM_TIMINGS doubles.
+ * counters (may be NULL, 8 doubles): [0] kernel launches per solve, [1] SOR launches,
+ * [2] SOR pixel-sweeps, [3] SOR ms at level 0, [4] SOR launches at level 0,
+ * [5] pixel-sweeps at level 0. */
+int pf_plan_profile(pf_plan* plan, double* timings, double* counters);
+
+/* ---- batches: N independent frame pairs sharded over devices, no collective ---
+ * pair p runs on devices[p % ndevices]; im1/im2/vx/vy/warpI2 are arrays of N host pointers. */
+int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* const* warpI2,
+                  const double* const* im1, const double* const* im2, double alpha, double ratio,
+                  int minWidth, int levels, int nOuterFPIterations, int nInnerFPIterations,
+                  int nSORIterations, int colType, int h, int w, int c, int mode,
+                  const int* devices, int ndevices, double* seconds);
+
+/* ---- single stages: the reference's public static functions (S/OpticalFlow.h:28-56) and the
+ *      Image/ImageProcessing primitives they use, one call each, for per-stage parity tests.
+ *      Same HWC float64 host buffers; `mode` selects the arithmetic (FP64 or FP32). ------------ */
+/* GaussianPyramid::ConstructPyramidLevels (S/GaussianPyramid.cpp:79-108); out = levels concatenated */
+int pf_stage_pyramid(double* out, const double* im, int h, int w, int c, double ratio, int levels,
+                     int mode, int device);
+/* OpticalFlow::im2feature (S/OpticalFlow.cpp:911-961); returns feature channel count (>0) */
+int pf_stage_im2feature(double* feat, const double* im, int h, int w, int c, int swap_luma,
+                        int mode, int device);
+/* OpticalFlow::getDxs (S/OpticalFlow.cpp:80-122) */
+int pf_stage_getdxs(double* imdx, double* imdy, double* imdt, const double* im1, const double* im2,
+                    int h, int w, int c, int mode, int device);
+/* OpticalFlow::warpFL (S/OpticalFlow.cpp:154-159 -> S/ImageProcessing.h:483-503) */
+int pf_stage_warpfl(double* warp, const double* im1, const double* im2, const double* vx,
+                    const double* vy, int h, int w, int c, int mode, int device);
+/* Image::imresize(dstW,dstH) + Multiplywith (S/Image.h:778-783,1841-1850): flow upsampling */
+int pf_stage_resize_to(double* dst, const double* src, int h, int w, int c, int dh, int dw,
+                       double scale, int mode, int device);
+/* Image::warpImageBicubicRef + threshold (S/Image.h:2587-2701, 2031-2045) */
+int pf_stage_bicubic(double* out, const double* ref, const double* im2, const double* vx,
+                     const double* vy, int h, int w, int c, int mode, int device);
+/* Linear-system assembly of one inner iteration (S/OpticalFlow.cpp:295-448); lap has c entries;
+ * du/dv may be NULL (zero).  Outputs are (h,w) planes. */
+int pf_stage_assemble(double* phi, double* dxy, double* dx2, double* dy2, double* bu, double* bv,
+                      const double* imdx, const double* imdy, const double* imdt, const double* u,
+                      const double* v, const double* du, const double* dv, const double* lap,
+                      double alpha, int h, int w, int c, int mode, int device);
+/* The SOR sweeps alone (S/OpticalFlow.cpp:451-505) from du=dv=0; ordering from `mode`. */
+int pf_stage_sor(double* du, double* dv, const double* phi, const double* dxy, const double* dx2,
+                 const double* dy2, const double* bu, const double* bv, double alpha, int nsor,
+                 int h, int w, int mode, int device);
+
+/* ---- micro-benchmark of the SOR kernel on resident synthetic coefficients (bench.py roofline) */
+int pf_bench_sor(int h, int w, int nsor, int repeats, int mode, int device, double* ms_per_solve,
+                 double* launches_per_solve);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFLOW_B200_H */

@@ -1,0 +1,10 @@
+"""B200-native drop-in for the `pyflow.coarse2fine_flow` hot path of
+ElijahHyndman/PAPTeam_OpticalFlow (Ce Liu's coarse-to-fine variational optical flow).
+
+The arithmetic lives in hand-written sm_100a CUDA kernels behind the C ABI declared in
+include/pyflow_b200.h (built into papteam_opticalflow_b200/libpyflow_b200.so); this package is the
+host-side mirror of the reference's Cython module (Par/pyflow.pyx).  There is no CPU fallback.
+"""
+from .pyflow import coarse2fine_flow, coarse2fine_flow_batch, FlowPlan, MODES  # noqa: F401
+
+__all__ = ["coarse2fine_flow", "coarse2fine_flow_batch", "FlowPlan", "MODES"]

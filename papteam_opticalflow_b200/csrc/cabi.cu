@@ -1,0 +1,357 @@
+// extern "C" surface declared in include/pyflow_b200.h.  Argument validation, error translation
+// and mode dispatch only; the work is in Plan<T> (solver.cuh) and Stages<T> (stages.cuh).
+#include <atomic>
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "factory.hpp"
+#include "geometry.hpp"
+#include "solver.cuh"
+
+using namespace pf;
+
+struct pf_plan {
+    std::unique_ptr<PlanBase> impl;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        g_err.clear();
+        return f();
+    } catch (const Error& e) {
+        cudaGetLastError();  // clear the sticky-less error state
+        return fail(e.code, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(PF_ENOMEM, "host allocation failed");
+    } catch (const std::exception& e) {
+        return fail(PF_ECUDA, e.what());
+    }
+}
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(PF_ENODEVICE, std::string("no usable CUDA device (") +
+                                      (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+                                      "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(PF_ENODEVICE, "device index " + std::to_string(device) + " out of range [0," + std::to_string(n) + ")");
+    return PF_OK;
+}
+
+int check_mode(int mode) {
+    if (mode < 0 || mode > 3) return fail(PF_EINVAL, "unknown mode " + std::to_string(mode));
+    return PF_OK;
+}
+
+int check_image(int h, int w, int c) {
+    if (h < 1 || w < 1 || c < 1) return fail(PF_EINVAL, "image dimensions must be positive");
+    if (c > 16) return fail(PF_EUNSUPPORTED, "more than 16 channels");
+    if ((long long)h * w > (1LL << 28)) return fail(PF_EUNSUPPORTED, "image too large");
+    return PF_OK;
+}
+
+PlanBase* make_plan(const Params& p) { return mode_is_fp64(p.mode) ? make_plan_f64(p) : make_plan_f32(p); }
+const StageCalls& stages(int mode) { return mode_is_fp64(mode) ? stages_f64() : stages_f32(); }
+
+int stage_prologue(int h, int w, int c, int mode, int device) {
+    int r;
+    if ((r = check_image(h, w, c)) || (r = check_mode(mode)) || (r = check_device(device))) return r;
+    PF_CUDA(cudaSetDevice(device));
+    return PF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pf_last_error(void) { return g_err.c_str(); }
+const char* pf_version(void) { return "pyflow_b200 0.1 (sm_100a)"; }
+
+int pf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void* pf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pf_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int pf_pyramid_levels(int width, double ratio, int minWidth) {
+    if (width < 1 || minWidth < 1) return fail(PF_EINVAL, "width and minWidth must be positive");
+    return levels_from_min_width(width, ratio, minWidth);
+}
+
+int pf_level_geometry(int w, int h, double ratio, int levels, int* widths, int* heights) {
+    if (w < 1 || h < 1 || levels < 1 || levels > 64 || !widths || !heights) return fail(PF_EINVAL, "bad geometry request");
+    std::vector<Level> g = level_geometry(w, h, ratio, levels);
+    for (int i = 0; i < levels; i++) {
+        widths[i] = g[(size_t)i].w;
+        heights[i] = g[(size_t)i].h;
+    }
+    return PF_OK;
+}
+
+int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                   int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!plan) return fail(PF_EINVAL, "plan is NULL");
+        *plan = nullptr;
+        int r;
+        if ((r = check_image(h, w, c)) || (r = check_mode(mode))) return r;
+        if (nOuter < 0 || nInner < 0 || nSOR < 0) return fail(PF_EINVAL, "iteration counts must be non-negative");
+        if (levels <= 0 && minWidth < 1) return fail(PF_EINVAL, "minWidth must be positive");
+        if (!(alpha == alpha) || !(ratio == ratio) || ratio <= 0) return fail(PF_EINVAL, "alpha/ratio invalid");
+        if ((r = check_device(device))) return r;
+        Params p{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, device};
+        std::unique_ptr<pf_plan> pl(new pf_plan);
+        pl->impl.reset(make_plan(p));
+        *plan = pl.release();
+        return PF_OK;
+    });
+}
+
+int pf_plan_destroy(pf_plan* plan) {
+    return guarded([&]() -> int {
+        delete plan;
+        return PF_OK;
+    });
+}
+
+int pf_plan_levels(const pf_plan* plan) { return plan ? plan->impl->levels() : PF_EINVAL; }
+
+int pf_plan_execute(pf_plan* plan, double* vx, double* vy, double* warpI2, const double* im1,
+                    const double* im2, double* timings) {
+    return guarded([&]() -> int {
+        if (!plan || !vx || !vy || !warpI2 || !im1 || !im2) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->execute(vx, vy, warpI2, im1, im2, timings);
+        return PF_OK;
+    });
+}
+
+int pf_plan_upload(pf_plan* plan, const double* im1, const double* im2) {
+    return guarded([&]() -> int {
+        if (!plan || !im1 || !im2) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->upload(im1, im2);
+        return PF_OK;
+    });
+}
+
+int pf_plan_solve(pf_plan* plan, int repeats, double* ms_total) {
+    return guarded([&]() -> int {
+        if (!plan || repeats < 1) return fail(PF_EINVAL, "bad argument");
+        plan->impl->solve(repeats, ms_total);
+        return PF_OK;
+    });
+}
+
+int pf_plan_download(pf_plan* plan, double* vx, double* vy, double* warpI2) {
+    return guarded([&]() -> int {
+        if (!plan || !vx || !vy || !warpI2) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->download(vx, vy, warpI2);
+        return PF_OK;
+    });
+}
+
+int pf_plan_profile(pf_plan* plan, double* timings, double* counters) {
+    return guarded([&]() -> int {
+        if (!plan || !timings) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->profile(timings, counters);
+        return PF_OK;
+    });
+}
+
+int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im1,
+                        const double* im2, double alpha, double ratio, int minWidth, int nOuter,
+                        int nInner, int nSOR, int colType, int h, int w, int c, int mode, int device,
+                        double* timings) {
+    pf_plan* pl = nullptr;
+    int r = pf_plan_create(&pl, h, w, c, alpha, ratio, minWidth, 0, nOuter, nInner, nSOR, colType, mode, device);
+    if (r) return r;
+    r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
+    std::string keep = g_err;
+    pf_plan_destroy(pl);
+    if (r) g_err = keep;
+    return r;
+}
+
+int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const double* im1,
+                               const double* im2, int pyramidLevels, int nCores, int h, int w, int c,
+                               int mode, int device, double* timings) {
+    (void)nCores;
+    if (pyramidLevels < 1) return fail(PF_EINVAL, "pyramidLevels must be >= 1");
+    pf_plan* pl = nullptr;
+    // hard-coded solver constants of the fork: S/OpticalFlow.cpp:747-751; colType 0: wrapper :22
+    int r = pf_plan_create(&pl, h, w, c, 0.012, 0.75, 20, pyramidLevels, 7, 1, 30, 0, mode, device);
+    if (r) return r;
+    r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
+    std::string keep = g_err;
+    pf_plan_destroy(pl);
+    if (r) g_err = keep;
+    return r;
+}
+
+int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* const* warpI2,
+                  const double* const* im1, const double* const* im2, double alpha, double ratio,
+                  int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h,
+                  int w, int c, int mode, const int* devices, int ndevices, double* seconds) {
+    if (npairs < 0 || ndevices < 1 || !devices) return fail(PF_EINVAL, "bad batch arguments");
+    if (npairs > 0 && (!vx || !vy || !warpI2 || !im1 || !im2)) return fail(PF_EINVAL, "NULL argument");
+    for (int d = 0; d < ndevices; d++) {
+        int r = check_device(devices[d]);
+        if (r) return r;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> workers;
+    std::vector<int> status((size_t)ndevices, PF_OK);
+    std::vector<std::string> messages((size_t)ndevices);
+    for (int d = 0; d < ndevices; d++) {
+        workers.emplace_back([&, d]() {
+            pf_plan* pl = nullptr;
+            int r = pf_plan_create(&pl, h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[d]);
+            for (int p = d; r == PF_OK && p < npairs; p += ndevices)
+                r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], nullptr);
+            if (r) messages[(size_t)d] = g_err;
+            if (pl) pf_plan_destroy(pl);
+            status[(size_t)d] = r;
+        });
+    }
+    for (auto& t : workers) t.join();
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int d = 0; d < ndevices; d++)
+        if (status[(size_t)d]) return fail(status[(size_t)d], messages[(size_t)d]);
+    return PF_OK;
+}
+
+// ---- single stages ---------------------------------------------------------------------------------
+int pf_stage_pyramid(double* out, const double* im, int h, int w, int c, double ratio, int levels, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!out || !im || levels < 1 || levels > 64) return fail(PF_EINVAL, "bad argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).pyramid(out, im, h, w, c, ratio, levels);
+        return PF_OK;
+    });
+}
+
+int pf_stage_im2feature(double* feat, const double* im, int h, int w, int c, int swap_luma, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!feat || !im) return fail(PF_EINVAL, "NULL argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        return stages(mode).im2feature(feat, im, h, w, c, swap_luma);
+    });
+}
+
+int pf_stage_getdxs(double* imdx, double* imdy, double* imdt, const double* im1, const double* im2, int h, int w, int c, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!imdx || !imdy || !imdt || !im1 || !im2) return fail(PF_EINVAL, "NULL argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).getdxs(imdx, imdy, imdt, im1, im2, h, w, c);
+        return PF_OK;
+    });
+}
+
+int pf_stage_warpfl(double* warp, const double* im1, const double* im2, const double* vx, const double* vy, int h, int w, int c, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!warp || !im1 || !im2 || !vx || !vy) return fail(PF_EINVAL, "NULL argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).warpfl(warp, im1, im2, vx, vy, h, w, c);
+        return PF_OK;
+    });
+}
+
+int pf_stage_resize_to(double* dst, const double* src, int h, int w, int c, int dh, int dw, double scale, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!dst || !src || dh < 1 || dw < 1) return fail(PF_EINVAL, "bad argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).resize_to(dst, src, h, w, c, dh, dw, scale);
+        return PF_OK;
+    });
+}
+
+int pf_stage_bicubic(double* out, const double* ref, const double* im2, const double* vx, const double* vy, int h, int w, int c, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!out || !ref || !im2 || !vx || !vy) return fail(PF_EINVAL, "NULL argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).bicubic(out, ref, im2, vx, vy, h, w, c);
+        return PF_OK;
+    });
+}
+
+int pf_stage_assemble(double* phi, double* dxy, double* dx2, double* dy2, double* bu, double* bv,
+                      const double* imdx, const double* imdy, const double* imdt, const double* u,
+                      const double* v, const double* du, const double* dv, const double* lap,
+                      double alpha, int h, int w, int c, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!phi || !dxy || !dx2 || !dy2 || !bu || !bv || !imdx || !imdy || !imdt || !u || !v) return fail(PF_EINVAL, "NULL argument");
+        int r = stage_prologue(h, w, c, mode, device);
+        if (r) return r;
+        stages(mode).assemble(phi, dxy, dx2, dy2, bu, bv, imdx, imdy, imdt, u, v, du, dv, lap, alpha, h, w, c);
+        return PF_OK;
+    });
+}
+
+int pf_stage_sor(double* du, double* dv, const double* phi, const double* dxy, const double* dx2,
+                 const double* dy2, const double* bu, const double* bv, double alpha, int nsor, int h,
+                 int w, int mode, int device) {
+    return guarded([&]() -> int {
+        if (!du || !dv || !phi || !dxy || !dx2 || !dy2 || !bu || !bv || nsor < 0) return fail(PF_EINVAL, "bad argument");
+        int r = stage_prologue(h, w, 1, mode, device);
+        if (r) return r;
+        stages(mode).sor(du, dv, phi, dxy, dx2, dy2, bu, bv, alpha, nsor, h, w, mode, device, 1, nullptr, nullptr);
+        return PF_OK;
+    });
+}
+
+int pf_bench_sor(int h, int w, int nsor, int repeats, int mode, int device, double* ms_per_solve, double* launches_per_solve) {
+    return guarded([&]() -> int {
+        if (nsor < 1 || repeats < 2) return fail(PF_EINVAL, "nsor >= 1 and repeats >= 2 required");
+        int r = stage_prologue(h, w, 1, mode, device);
+        if (r) return r;
+        // synthetic but well-conditioned coefficients (positive weights, diagonally dominant system)
+        size_t n = (size_t)h * w;
+        std::vector<double> phi(n), dxy(n), dx2(n), dy2(n), bu(n), bv(n);
+        unsigned s = 12345u;
+        auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (double)(s >> 8) / 16777216.0; };
+        for (size_t i = 0; i < n; i++) {
+            phi[i] = 0.5 + 20 * rnd(); dxy[i] = 0.2 * (rnd() - 0.5); dx2[i] = 0.1 + rnd(); dy2[i] = 0.1 + rnd();
+            bu[i] = rnd() - 0.5; bv[i] = rnd() - 0.5;
+        }
+        stages(mode).sor(nullptr, nullptr, phi.data(), dxy.data(), dx2.data(), dy2.data(), bu.data(), bv.data(),
+                         0.012, nsor, h, w, mode, device, repeats, ms_per_solve, launches_per_solve);
+        return PF_OK;
+    });
+}
+
+}  // extern "C"

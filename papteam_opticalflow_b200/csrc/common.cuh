@@ -1,0 +1,74 @@
+// Shared host/device definitions for the B200 optical-flow solver.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/pyflow_b200.h"
+
+namespace pf {
+
+// ---- error plumbing: CUDA failures become exceptions, the C ABI turns them into PF_ECUDA -----
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PF_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            throw pf::Error(_e == cudaErrorMemoryAllocation ? PF_ENOMEM : PF_ECUDA,           \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                                __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    } while (0)
+
+#define PF_CHECK_LAUNCH() PF_CUDA(cudaGetLastError())
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- planar image view --------------------------------------------------------------------------
+// HBM layout: channel-planar (SoA), rows padded to a pitch of 32 elements (128 B in FP32, 256 B in
+// FP64) so every row starts on a cache-line boundary and float4/double2 accesses stay aligned.
+// The reference's HWC interleaving (S/Image.h:36-461) exists only at the import/export kernels.
+template <typename T>
+struct Img {
+    T* p = nullptr;
+    int w = 0, h = 0, c = 0;
+    int pitch = 0;       // elements per row
+    size_t plane = 0;    // elements per channel plane
+    __host__ __device__ T* ch(int k) const { return p + (size_t)k * plane; }
+    __host__ __device__ size_t elems() const { return plane * (size_t)c; }
+};
+
+constexpr int kPitchAlign = 32;
+inline int pitch_for(int w) { return (int)round_up((size_t)w, kPitchAlign); }
+inline size_t plane_for(int w, int h) { return round_up((size_t)pitch_for(w) * h, 64); }
+
+// up to 2*8+1 filter taps passed by value in kernel parameters
+constexpr int kMaxHalf = 8;
+template <typename T>
+struct Taps {
+    T v[2 * kMaxHalf + 1];
+    int half;
+};
+
+// solver parameters after the boundary has normalised both call shapes
+struct Params {
+    int h, w, c;
+    double alpha, ratio;
+    int min_width, levels;   // levels > 0 wins
+    int n_outer, n_inner, n_sor;
+    int col_type;
+    int mode, device;
+};
+
+inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }
+inline bool mode_is_lex(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP32_WAVEFRONT; }
+
+}  // namespace pf

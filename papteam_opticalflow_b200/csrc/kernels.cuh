@@ -1,0 +1,419 @@
+// Elementwise / stencil / gather kernels of the solver, templated on the arithmetic type
+// (float for the fast mode, double for the parity mode).  In the double instantiation every
+// expression keeps the reference's operation order (the translation unit is compiled with
+// -fmad=false), so results agree with the reference at the bit level; see SURVEY.md Appendix A.
+// Citations: S/ = /root/reference/Code/Serial/src/.
+#pragma once
+#include "common.cuh"
+
+namespace pf {
+
+__device__ __forceinline__ int clampi(int v, int n) { return min(max(v, 0), n - 1); }
+
+// ---------------------------------------------------------------------------------------------
+// Boundary conversion: HWC float64 (the numpy buffer, P/Coarse2FineFlowWrapper.cpp:23-26) <-> planar T
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_import_hwc(const double* __restrict__ src, Img<T> dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst.w) return;
+    const double* s = src + ((size_t)y * dst.w + x) * dst.c;
+    for (int k = 0; k < dst.c; k++) dst.ch(k)[(size_t)y * dst.pitch + x] = (T)s[k];
+}
+
+template <typename T>
+__global__ void k_export_hwc(Img<T> src, double* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= src.w) return;
+    double* d = dst + ((size_t)y * src.w + x) * src.c;
+    for (int k = 0; k < src.c; k++) d[k] = (double)src.ch(k)[(size_t)y * src.pitch + x];
+}
+
+template <typename T>
+__global__ void k_fill(Img<T> img, T value) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= img.w) return;
+    img.ch(k)[(size_t)y * img.pitch + x] = value;
+}
+
+template <typename T>
+__global__ void k_copy(Img<T> src, Img<T> dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= src.w) return;
+    dst.ch(k)[(size_t)y * dst.pitch + x] = src.ch(k)[(size_t)y * src.pitch + x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-D correlation with replicate borders (S/ImageProcessing.h:259-279, :350-369):
+//   dst(p) = sum_{l=-f..f} tap[l+f] * src(clamp(p+l)), ascending l, accumulator starts at 0.
+// One thread per output element; channels on blockIdx.z.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_filter_h(Img<T> src, Img<T> dst, Taps<T> t) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= src.w) return;
+    const T* s = src.ch(k) + (size_t)y * src.pitch;
+    T acc = 0;
+    for (int l = -t.half; l <= t.half; l++) acc += s[clampi(x + l, src.w)] * t.v[l + t.half];
+    dst.ch(k)[(size_t)y * dst.pitch + x] = acc;
+}
+
+template <typename T>
+__global__ void k_filter_v(Img<T> src, Img<T> dst, Taps<T> t) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= src.w) return;
+    const T* s = src.ch(k);
+    T acc = 0;
+    for (int l = -t.half; l <= t.half; l++)
+        acc += s[(size_t)clampi(y + l, src.h) * src.pitch + x] * t.v[l + t.half];
+    dst.ch(k)[(size_t)y * dst.pitch + x] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear sampler (S/ImageProcessing.h:138-157).  Coordinates stay in double in BOTH modes
+// (x = j + u at j ~ 3840 has only 2.4e-4 px resolution in FP32): the integer
+// part comes from C truncation toward zero, the fraction is clamped to [0,1], taps are
+// index-clamped and visited in the order (m,n) = (0,0),(0,1),(1,0),(1,1), m being the x offset.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Bilin {
+    int x0, x1, y0, y1;
+    T w00, w01, w10, w11;  // w[m][n]
+    __device__ __forceinline__ Bilin(double x, double y, int w, int h) {
+        int xi = (int)x, yi = (int)y;
+        double fx = x - xi, fy = y - yi;
+        fx = fmax(fmin(fx, 1.0), 0.0);
+        fy = fmax(fmin(fy, 1.0), 0.0);
+        x0 = clampi(xi, w); x1 = clampi(xi + 1, w);
+        y0 = clampi(yi, h); y1 = clampi(yi + 1, h);
+        T ax0 = (T)fabs(1 - fx), ax1 = (T)fabs(0 - fx);   // |1-m-dx|, m = 0,1
+        T ay0 = (T)fabs(1 - fy), ay1 = (T)fabs(0 - fy);
+        w00 = ax0 * ay0; w01 = ax0 * ay1; w10 = ax1 * ay0; w11 = ax1 * ay1;
+    }
+    __device__ __forceinline__ T sample(const T* __restrict__ p, int pitch) const {
+        T acc = 0;
+        acc += p[(size_t)y0 * pitch + x0] * w00;
+        acc += p[(size_t)y1 * pitch + x0] * w01;
+        acc += p[(size_t)y0 * pitch + x1] * w10;
+        acc += p[(size_t)y1 * pitch + x1] * w11;
+        return acc;
+    }
+};
+
+// Bilinear resize (S/ImageProcessing.h:214-253): source coordinate (j+1)/r - 1 with per-axis
+// ratios rx, ry; `scale` folds the caller's Multiplywith (flow upsampling, S/OpticalFlow.cpp:809-812).
+template <typename T>
+__global__ void k_resize(Img<T> src, Img<T> dst, double rx, double ry, T scale, int apply_scale) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst.w) return;
+    double sx = (double)(x + 1) / rx - 1, sy = (double)(y + 1) / ry - 1;
+    Bilin<T> b(sx, sy, src.w, src.h);
+    for (int k = 0; k < src.c; k++) {
+        T v = b.sample(src.ch(k), src.pitch);
+        if (apply_scale) v *= scale;
+        dst.ch(k)[(size_t)y * dst.pitch + x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2feature (S/OpticalFlow.cpp:911-961): RGB -> [gray, d/dx gray, d/dy gray, G-R, G-B];
+// gray -> [I, Ix, Iy].  Luma (S/Image.h:1461-1480) is evaluated left to right; the derivative is the
+// 5-tap [1,-8,0,8,-1]/12 correlation with replicate borders (S/Image.h:987-993, 1030-1036), computed
+// here by re-evaluating the luma at the eight neighbours (same arithmetic, no intermediate plane).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T luma_at(const Img<T>& im, int x, int y, int swap) {
+    size_t o = (size_t)y * im.pitch + x;
+    if (im.c == 1) return im.ch(0)[o];
+    T r = im.ch(0)[o], g = im.ch(1)[o], b = im.ch(2)[o];
+    return swap ? r * (T).114 + g * (T).587 + b * (T).299 : r * (T).299 + g * (T).587 + b * (T).114;
+}
+
+template <typename T>
+__global__ void k_im2feature(Img<T> im, Img<T> feat, Taps<T> d5, int swap) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= im.w) return;
+    size_t o = (size_t)y * feat.pitch + x;
+    T gx = 0, gy = 0;
+    for (int l = -2; l <= 2; l++) gx += luma_at(im, clampi(x + l, im.w), y, swap) * d5.v[l + 2];
+    for (int l = -2; l <= 2; l++) gy += luma_at(im, x, clampi(y + l, im.h), swap) * d5.v[l + 2];
+    feat.ch(0)[o] = luma_at(im, x, y, swap);
+    feat.ch(1)[o] = gx;
+    feat.ch(2)[o] = gy;
+    if (im.c == 3) {
+        size_t oi = (size_t)y * im.pitch + x;
+        T r = im.ch(0)[oi], g = im.ch(1)[oi], b = im.ch(2)[oi];
+        feat.ch(3)[o] = g - r;
+        feat.ch(4)[o] = g - b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear warp with Im1 fallback outside the image (S/ImageProcessing.h:483-503), optionally
+// preceded by the flow update u += du, v += dv of S/OpticalFlow.cpp:513-514 (du == nullptr: none).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
+                              T* __restrict__ v, const T* __restrict__ du,
+                              const T* __restrict__ dv, int fpitch) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= im1.w) return;
+    size_t of = (size_t)y * fpitch + x;
+    T uu = u[of], vv = v[of];
+    if (du) {
+        uu += du[of];
+        vv += dv[of];
+        u[of] = uu;
+        v[of] = vv;
+    }
+    double sx = (double)x + (double)uu, sy = (double)y + (double)vv;
+    size_t o = (size_t)y * im1.pitch + x;
+    if (sx < 0 || sx > im1.w - 1 || sy < 0 || sy > im1.h - 1) {
+        for (int k = 0; k < im1.c; k++) warp.ch(k)[o] = im1.ch(k)[o];
+        return;
+    }
+    Bilin<T> b(sx, sy, im1.w, im1.h);
+    for (int k = 0; k < im1.c; k++) warp.ch(k)[o] = b.sample(im2.ch(k), im2.pitch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// getDxs pieces (S/OpticalFlow.cpp:80-122): blend = Im1s*0.4 + Im2s*0.6 ; imdt = Im2s - Im1s
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_blend_dt(Img<T> s1, Img<T> s2, Img<T> blend, Img<T> dt) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+    if (x >= s1.w) return;
+    size_t o = (size_t)y * s1.pitch + x;
+    T a = s1.ch(k)[o], b = s2.ch(k)[o];
+    T t = a * (T)0.4;
+    blend.ch(k)[o] = t + b * (T)0.6;
+    dt.ch(k)[o] = b - a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phi (S/OpticalFlow.cpp:295-331): forward differences of uu = u + du (last column / last row
+// zero, S/Image.h:969-986, 1013-1029), phi = 0.5 / sqrt(ux^2 + uy^2 + vx^2 + vy^2 + eps)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_phi(const T* __restrict__ u, const T* __restrict__ v, const T* __restrict__ du,
+                      const T* __restrict__ dv, T* __restrict__ phi, int w, int h, int pitch,
+                      T eps) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    size_t o = (size_t)y * pitch + x;
+    auto U = [&](size_t i) { return du ? u[i] + du[i] : u[i]; };
+    auto V = [&](size_t i) { return dv ? v[i] + dv[i] : v[i]; };
+    T u0 = U(o), v0 = V(o);
+    T ux = 0, uy = 0, vx = 0, vy = 0;
+    if (x < w - 1) { ux = U(o + 1) - u0; vx = V(o + 1) - v0; }
+    if (y < h - 1) { uy = U(o + pitch) - u0; vy = V(o + pitch) - v0; }
+    T t = ux * ux + uy * uy + vx * vx + vy * vy;
+    phi[o] = (T)0.5 / sqrt(t + eps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Linear-system assembly (S/OpticalFlow.cpp:333-448 + the loop-invariant part of :463-504):
+//   psi_k  = 1 / (2 sqrt((It + Ix du + Iy dv)^2 + eps))        unless lap[k] < 1e-20  (:399-402)
+//   dxy    = mean_k (psi Ix) Iy, dx2, dy2, dtdx, dtdy likewise  (:414-427, S/Image.h:1536-1543)
+//   bu     = -dtdx - alpha * L(u),  bv = -dtdy - alpha * L(v)   (:444-448) with the fork's fused
+//            Laplacian that drops the inflow of the last column / last row (:641-690, quirk F3)
+//   iu     = omega / (dx2 + alpha*0.05 + alpha * sum_nbr phi)   (:496-501), iv likewise with dy2
+// iu/iv are exactly the `omega/(...)` sub-expression the reference evaluates first in :501/:504,
+// so precomputing them changes no rounding.  dx2/dy2 are written only when requested (stage tests).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct AssembleArgs {
+    Img<T> imdx, imdy, imdt;
+    const T *u, *v, *du, *dv, *phi;
+    const double* lap;  // per-channel Laplacian noise scale (device), may be nullptr
+    T *dxy, *iu, *iv, *bu, *bv, *dx2, *dy2;
+    int w, h, pitch;
+    T alpha, omega, eps;
+};
+
+template <typename T>
+__device__ __forceinline__ T laplacian_at(const T* __restrict__ in, const T* __restrict__ phi,
+                                          size_t o, int x, int y, int w, int h, int pitch) {
+    T out = 0;
+    if (x < w - 1) {
+        out -= (in[o + 1] - in[o]) * phi[o];
+        if (x > 0) out += (in[o] - in[o - 1]) * phi[o - 1];
+    }
+    if (y < h - 1) {
+        out -= (in[o + pitch] - in[o]) * phi[o];
+        if (y > 0) out += (in[o] - in[o - pitch]) * phi[o - pitch];
+    }
+    return out;
+}
+
+template <typename T>
+__global__ void k_assemble(AssembleArgs<T> a) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w) return;
+    size_t o = (size_t)y * a.pitch + x;
+    T du = a.du ? a.du[o] : (T)0, dv = a.dv ? a.dv[o] : (T)0;
+    T sxy = 0, sx2 = 0, sy2 = 0, stx = 0, sty = 0;
+    int C = a.imdx.c;
+    for (int k = 0; k < C; k++) {
+        size_t oc = (size_t)y * a.imdx.pitch + x;
+        T ix = a.imdx.ch(k)[oc], iy = a.imdy.ch(k)[oc], it = a.imdt.ch(k)[oc];
+        T psi = 0;
+        if (!(a.lap && a.lap[k] < 1e-20)) {
+            T t = it + ix * du + iy * dv;
+            t *= t;
+            psi = (T)1 / ((T)2 * sqrt(t + a.eps));
+        }
+        T px = psi * ix, py = psi * iy;
+        sxy += px * iy;
+        sx2 += px * ix;
+        sy2 += py * iy;
+        stx += px * it;
+        sty += py * it;
+    }
+    if (C > 1) {
+        T n = (T)C;
+        sxy /= n; sx2 /= n; sy2 /= n; stx /= n; sty /= n;
+    }
+    T lu = laplacian_at(a.u, a.phi, o, x, y, a.w, a.h, a.pitch);
+    T lv = laplacian_at(a.v, a.phi, o, x, y, a.w, a.h, a.pitch);
+    T cf = 0;
+    if (x > 0) cf += a.phi[o - 1];
+    if (x < a.w - 1) cf += a.phi[o];
+    if (y > 0) cf += a.phi[o - a.pitch];
+    if (y < a.h - 1) cf += a.phi[o];
+    cf *= a.alpha;
+    T reg = a.alpha * (T)0.05;
+    a.dxy[o] = sxy;
+    a.iu[o] = a.omega / (sx2 + reg + cf);
+    a.iv[o] = a.omega / (sy2 + reg + cf);
+    a.bu[o] = -stx - a.alpha * lu;
+    a.bv[o] = -sty - a.alpha * lv;
+    if (a.dx2) { a.dx2[o] = sx2; a.dy2[o] = sy2; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// estLaplacianNoise (S/OpticalFlow.cpp:594-639): per-channel mean of d = |Im1 - warpIm2| over
+// 0 < d < 1e6, 0.001 if none.  Its only consumer is the `< 1e-20` guard above, so the summation
+// order (block tree + atomics here) is immaterial.  acc = [sum_0..sum_C-1, cnt_0..cnt_C-1].
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_noise_accum(Img<T> a, Img<T> b, double* __restrict__ acc) {
+    int k = blockIdx.z;
+    double s = 0, n = 0;
+    for (int y = blockIdx.y; y < a.h; y += gridDim.y)
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.w; x += gridDim.x * blockDim.x) {
+            size_t o = (size_t)y * a.pitch + x;
+            double d = fabs((double)a.ch(k)[o] - (double)b.ch(k)[o]);
+            if (d > 0 && d < 1000000) { s += d; n += 1; }
+        }
+    for (int off = 16; off; off >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, off);
+        n += __shfl_down_sync(0xffffffffu, n, off);
+    }
+    if ((threadIdx.x & 31) == 0 && n > 0) {
+        atomicAdd(acc + k, s);
+        atomicAdd(acc + a.c + k, n);
+    }
+}
+
+static __global__ void k_noise_final(double* acc, double* lap, int c) {
+    int k = threadIdx.x;
+    if (k >= c) return;
+    lap[k] = acc[c + k] == 0 ? 0.001 : acc[k] / acc[c + k];
+    acc[k] = 0;
+    acc[c + k] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final output warp (S/Image.h:2624-2701 with coefficients :2497-2530, then threshold :2031-2045):
+// Hermite-bicubic from I, Ix, Iy, Ixy at the four clamped corners, Im1 fallback outside the image,
+// clamp to [0,1], written straight into the HWC float64 output buffer.
+// The 16 coefficients are integer combinations of the 16 corner samples; sources are indexed
+// 4*quantity + corner (quantity I,Ix,Iy,Ixy; corner 00,10,01,11, x digit first) and summed in the
+// listed order, which is the reference's left-to-right evaluation order.
+// ---------------------------------------------------------------------------------------------
+struct BicubicTable {
+    signed char n[16];
+    signed char src[16][16];
+    signed char wt[16][16];
+};
+
+template <typename T>
+__global__ void k_bicubic_warp(Img<T> ref, Img<T> im, Img<T> ix, Img<T> iy, Img<T> ixy,
+                               const T* __restrict__ u, const T* __restrict__ v, int fpitch,
+                               const BicubicTable* __restrict__ tab, double* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= im.w) return;
+    int w = im.w, h = im.h, C = im.c;
+    size_t of = (size_t)y * fpitch + x;
+    double sx = (double)x + (double)u[of], sy = (double)y + (double)v[of];
+    double* o = out + ((size_t)y * w + x) * C;
+    if (sx < 0 || sx > w - 1 || sy < 0 || sy > h - 1) {
+        for (int k = 0; k < C; k++) {
+            T r = ref.ch(k)[(size_t)y * ref.pitch + x];
+            o[k] = (double)min(max(r, (T)0), (T)1);
+        }
+        return;
+    }
+    int x0 = clampi((int)sx, w), x1 = clampi((int)sx + 1, w);
+    int y0 = clampi((int)sy, h), y1 = clampi((int)sy + 1, h);
+    T dx = (T)(sx - x0), dy = (T)(sy - y0);
+    T dx2 = dx * dx, dy2 = dy * dy, dx3 = dx * dx2, dy3 = dy * dy2;
+    size_t corner[4] = {(size_t)y0 * im.pitch + x0, (size_t)y0 * im.pitch + x1,
+                        (size_t)y1 * im.pitch + x0, (size_t)y1 * im.pitch + x1};
+    for (int k = 0; k < C; k++) {
+        T s[16];
+        const T* q[4] = {im.ch(k), ix.ch(k), iy.ch(k), ixy.ch(k)};
+#pragma unroll
+        for (int t = 0; t < 16; t++) s[t] = q[t >> 2][corner[t & 3]];
+        T a[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            T acc = (T)tab->wt[r][0] * s[tab->src[r][0]];
+            for (int t = 1; t < tab->n[r]; t++) acc += (T)tab->wt[r][t] * s[tab->src[r][t]];
+            a[r] = acc;
+        }
+        // a[4*i + j] multiplies dx^i dy^j; evaluation order of S/Image.h:2688-2691
+        T val = a[0] + a[1] * dy + a[2] * dy2 + a[3] * dy3 +
+                a[4] * dx + a[5] * dx * dy + a[6] * dx * dy2 + a[7] * dx * dy3 +
+                a[8] * dx2 + a[9] * dx2 * dy + a[10] * dx2 * dy2 + a[11] * dx2 * dy3 +
+                a[12] * dx3 + a[13] * dx3 * dy + a[14] * dx3 * dy2 + a[15] * dx3 * dy3;
+        o[k] = (double)min(max(val, (T)0), (T)1);
+    }
+}
+
+// Host-side definition of the table (shared by both instantiations).
+inline BicubicTable make_bicubic_table() {
+    enum { P00, P10, P01, P11, X00, X10, X01, X11, Y00, Y10, Y01, Y11, Z00, Z10, Z01, Z11 };
+    BicubicTable t;
+    memset(&t, 0, sizeof(t));
+    auto set = [&](int r, std::initializer_list<int> src, std::initializer_list<int> wt) {
+        t.n[r] = (signed char)src.size();
+        int i = 0;
+        for (int s : src) t.src[r][i++] = (signed char)s;
+        i = 0;
+        for (int w : wt) t.wt[r][i++] = (signed char)w;
+    };
+    const std::initializer_list<int> all = {P00, P10, P01, P11, X00, X10, X01, X11,
+                                            Y00, Y10, Y01, Y11, Z00, Z10, Z01, Z11};
+    // row index = 4*i + j for a[i][j]  (S/Image.h:2499-2529)
+    set(0, {P00}, {1});
+    set(1, {Y00}, {1});
+    set(2, {P00, P01, Y00, Y01}, {-3, 3, -2, -1});
+    set(3, {P00, P01, Y00, Y01}, {2, -2, 1, 1});
+    set(4, {X00}, {1});
+    set(5, {Z00}, {1});
+    set(6, {X00, X01, Z00, Z01}, {-3, 3, -2, -1});
+    set(7, {X00, X01, Z00, Z01}, {2, -2, 1, 1});
+    set(8, {P00, P10, X00, X10}, {-3, 3, -2, -1});
+    set(9, {Y00, Y10, Z00, Z10}, {-3, 3, -2, -1});
+    set(10, all, {9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1});
+    set(11, all, {-6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1});
+    set(12, {P00, P10, X00, X10}, {2, -2, 1, 1});
+    set(13, {Y00, Y10, Z00, Z10}, {2, -2, 1, 1});
+    set(14, all, {-6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1});
+    set(15, all, {4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1});
+    return t;
+}
+
+}  // namespace pf

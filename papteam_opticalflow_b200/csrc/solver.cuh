@@ -1,0 +1,593 @@
+// Plan<T>: device arena + launch sequence of one coarse-to-fine solve
+// (level driver S/OpticalFlow.cpp:735-846, SmoothFlowSOR :238-536), instantiated for float
+// (fast mode) and double (parity mode).  Host code only orchestrates: all arithmetic is in
+// kernels.cuh / sor.cuh.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <tuple>
+
+#include "common.cuh"
+#include "geometry.hpp"
+#include "kernels.cuh"
+#include "sor.cuh"
+
+namespace pf {
+
+// ---- abstract plan the C ABI talks to -----------------------------------------------------------
+struct PlanBase {
+    virtual ~PlanBase() {}
+    virtual int levels() const = 0;
+    virtual void upload(const double* im1, const double* im2) = 0;
+    virtual void solve(int repeats, double* ms_total) = 0;
+    virtual void download(double* vx, double* vy, double* warp) = 0;
+    virtual void execute(double* vx, double* vy, double* warp, const double* im1,
+                         const double* im2, double* timings) = 0;
+    virtual void profile(double* timings, double* counters) = 0;
+};
+
+// ---- simple bump allocator over one cudaMalloc ---------------------------------------------------
+class Arena {
+  public:
+    ~Arena() { release(); }
+    void reserve(size_t bytes) {
+        release();
+        PF_CUDA(cudaMalloc(&base_, bytes));
+        cap_ = bytes;
+        off_ = 0;
+    }
+    void release() {
+        if (base_) cudaFree(base_);
+        base_ = nullptr;
+        cap_ = off_ = 0;
+    }
+    template <typename U>
+    U* take(size_t n) {
+        size_t bytes = round_up(n * sizeof(U), 256);
+        if (off_ + bytes > cap_) throw Error(PF_ENOMEM, "arena overflow");
+        U* p = reinterpret_cast<U*>(static_cast<char*>(base_) + off_);
+        off_ += bytes;
+        return p;
+    }
+    static size_t need(size_t n, size_t elem) { return round_up(n * elem, 256); }
+
+  private:
+    void* base_ = nullptr;
+    size_t cap_ = 0, off_ = 0;
+};
+
+struct Span {
+    int phase, level;
+    cudaEvent_t a, b;
+};
+
+template <typename T>
+Taps<T> make_taps(const double* v, int half) {
+    if (half > kMaxHalf) throw Error(PF_EUNSUPPORTED, "Gaussian half-width > 8 not supported");
+    Taps<T> t;
+    t.half = half;
+    for (int i = 0; i < 2 * kMaxHalf + 1; i++) t.v[i] = 0;
+    for (int i = 0; i < 2 * half + 1; i++) t.v[i] = (T)v[i];
+    return t;
+}
+
+// Sweeps fused per launch of the tile kernel: whole solve if the image fits one region, otherwise
+// the value minimising a two-term cost model (bytes per pass + instruction issue per half-sweep).
+inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced) {
+    if (w <= kSorRegionW && h <= region_h) return nsor;
+    if (forced > 0) return std::min(forced, nsor);
+    double best = 1e300;
+    int best_t = 1;
+    for (int t = 1; t <= std::min(nsor, 8); t++) {
+        SorTiling tx = sor_tiling(w, kSorRegionW, 2 * t), ty = sor_tiling(h, region_h, 2 * t);
+        if (tx.ntiles == 0 || ty.ntiles == 0) break;
+        double ctas = (double)tx.ntiles * ty.ntiles;
+        double waves = std::ceil(ctas / 148.0);
+        double per_cta = 6000.0 + 2.0 * t * 450.0;  // load/store phase + 2t half-sweeps, in clocks
+        double passes = std::ceil((double)nsor / t);
+        double cost = passes * (waves * per_cta + 4000.0);
+        if (cost < best) { best = cost; best_t = t; }
+    }
+    return best_t;
+}
+
+
+// ---- SOR dispatch shared by the Plan and the single-stage entry points ---------------------------
+// Solves from du = dv = 0 and leaves the result in du/dv (the ping-pong pointers may be swapped).
+template <typename T>
+struct SorRunner {
+    static constexpr bool kF64 = sizeof(T) == 8;
+    // tile-kernel shape: FP32 64x64 regions (R=4, 16 warps), FP64 64x32 (R=2)
+    static constexpr int kR = kF64 ? 2 : 4;
+    static constexpr int kNW = 16;
+    static constexpr int kRegionH = kR * kNW;
+    bool lex = false, simple_rb = false;
+    int forced_fuse = 0, coop_max_blocks = 1;
+    cudaStream_t st = nullptr;
+
+    void init(int mode, int device, cudaStream_t stream) {
+        lex = mode_is_lex(mode);
+        st = stream;
+        const char* e = getenv("PF_SOR_FUSE");
+        forced_fuse = e ? atoi(e) : 0;
+        e = getenv("PF_SOR_SIMPLE");
+        simple_rb = e && atoi(e);
+        if (lex) {
+            int sms = 0, coop = 0, per_sm = 0;
+            PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            if (!coop) throw Error(PF_EUNSUPPORTED, "device lacks cooperative launch");
+            PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_wavefront<T>, 256, 0));
+            coop_max_blocks = std::max(1, per_sm * sms);
+        }
+    }
+
+    // returns the number of kernel launches
+    int run(SorArgs<T> a, T*& du, T*& dv, T*& du2, T*& dv2, int nsor) {
+        const int w = a.w, h = a.h;
+        size_t bytes = plane_for(w, h) * sizeof(T);
+        PF_CUDA(cudaMemsetAsync(du, 0, bytes, st));
+        PF_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
+        int launches = 0;
+        if (lex) {
+            a.du = du; a.dv = dv; a.du_in = nullptr; a.dv_in = nullptr;
+            long long work = (long long)nsor * std::min(w, h);
+            int blocks = (int)std::min<long long>(coop_max_blocks, std::max<long long>(1, (work + 255) / 256));
+            void* args[] = {&a, &nsor};
+            PF_CUDA(cudaLaunchCooperativeKernel((void*)k_sor_wavefront<T>, dim3(blocks), dim3(256), args, 0, st));
+            return 1;
+        }
+        if (simple_rb) {
+            a.du = du; a.dv = dv; a.du_in = nullptr; a.dv_in = nullptr;
+            for (int s = 0; s < nsor; s++)
+                for (int c = 0; c < 2; c++) {
+                    k_sor_rb_half<T><<<dim3(ceil_div(ceil_div(w, 2) + 1, 128), h), 128, 0, st>>>(a, c);
+                    launches++;
+                }
+            return launches;
+        }
+        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse);
+        int done = 0;
+        while (done < nsor) {
+            int nsw = std::min(fuse, nsor - done);
+            SorTiling tx = sor_tiling(w, kSorRegionW, 2 * nsw), ty = sor_tiling(h, kRegionH, 2 * nsw);
+            if (tx.ntiles == 0 || ty.ntiles == 0) throw Error(PF_EINVAL, "SOR tiling failed");
+            a.du_in = du; a.dv_in = dv; a.du = du2; a.dv = dv2;
+            k_sor_rb_tile<T, kR, kNW><<<dim3(tx.ntiles, ty.ntiles), kNW * 32, 0, st>>>(a, nsw, tx.step, ty.step);
+            launches++;
+            std::swap(du, du2);
+            std::swap(dv, dv2);
+            done += nsw;
+        }
+        return launches;
+    }
+};
+
+template <typename T>
+class Plan : public PlanBase {
+  public:
+    static constexpr bool kF64 = sizeof(T) == 8;
+
+    explicit Plan(const Params& p) : P(p) {
+        lex_ = mode_is_lex(P.mode);
+        PF_CUDA(cudaSetDevice(P.device));
+        nlev_ = P.levels > 0 ? P.levels : levels_from_min_width(P.w, P.ratio, P.min_width);
+        if (nlev_ < 1 || nlev_ > 64) throw Error(PF_EINVAL, "pyramid level count out of range (got " + std::to_string(nlev_) + ")");
+        geo_ = level_geometry(P.w, P.h, P.ratio, nlev_);
+        for (auto& g : geo_)
+            if (g.w < 1 || g.h < 1) throw Error(PF_EINVAL, "pyramid level collapsed to zero size");
+        fc_ = P.c == 1 ? 3 : (P.c == 3 ? 5 : P.c);
+        if (fc_ > 16) throw Error(PF_EUNSUPPORTED, "more than 16 channels");
+        const char* e = getenv("PF_NO_GRAPH");
+        use_graph_ = !(e && atoi(e)) && !lex_;
+        PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
+        allocate();
+        sor_.init(P.mode, P.device, st_);
+    }
+
+    ~Plan() override {
+        cudaSetDevice(P.device);
+        if (gexec_) cudaGraphExecDestroy(gexec_);
+        if (graph_) cudaGraphDestroy(graph_);
+        for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
+        if (st_) cudaStreamDestroy(st_);
+    }
+
+    int levels() const override { return nlev_; }
+
+    void upload(const double* im1, const double* im2) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        size_t n = (size_t)P.h * P.w * P.c * sizeof(double);
+        PF_CUDA(cudaMemcpyAsync(d_in1_, im1, n, cudaMemcpyHostToDevice, st_));
+        PF_CUDA(cudaMemcpyAsync(d_in2_, im2, n, cudaMemcpyHostToDevice, st_));
+    }
+
+    void download(double* vx, double* vy, double* warp) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        size_t n = (size_t)P.h * P.w * sizeof(double);
+        PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaMemcpyAsync(vy, d_vy_, n, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaMemcpyAsync(warp, d_warp_, n * P.c, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaStreamSynchronize(st_));
+    }
+
+    // device-only solve, `repeats` times back to back, timed with events on the launching stream
+    void solve(int repeats, double* ms_total) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        PF_CUDA(cudaEventRecord(ev_[0], st_));
+        for (int i = 0; i < repeats; i++) run_solve();
+        PF_CUDA(cudaEventRecord(ev_[1], st_));
+        PF_CUDA(cudaStreamSynchronize(st_));
+        float ms = 0;
+        PF_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        if (ms_total) *ms_total = ms;
+    }
+
+    void execute(double* vx, double* vy, double* warp, const double* im1, const double* im2,
+                 double* timings) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        PF_CUDA(cudaEventRecord(ev_[0], st_));
+        upload(im1, im2);
+        PF_CUDA(cudaEventRecord(ev_[1], st_));
+        run_solve();
+        PF_CUDA(cudaEventRecord(ev_[2], st_));
+        size_t n = (size_t)P.h * P.w * sizeof(double);
+        PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaMemcpyAsync(vy, d_vy_, n, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaMemcpyAsync(warp, d_warp_, n * P.c, cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaEventRecord(ev_[3], st_));
+        PF_CUDA(cudaStreamSynchronize(st_));
+        if (timings) {
+            for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
+            float a = 0, b = 0, c = 0, d = 0;
+            PF_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[3]));
+            PF_CUDA(cudaEventElapsedTime(&b, ev_[0], ev_[1]));
+            PF_CUDA(cudaEventElapsedTime(&c, ev_[1], ev_[2]));
+            PF_CUDA(cudaEventElapsedTime(&d, ev_[2], ev_[3]));
+            timings[PF_T_TOTAL] = a;
+            timings[PF_T_H2D] = b;
+            timings[PF_T_SOLVE] = c;
+            timings[PF_T_D2H] = d;
+        }
+    }
+
+    // eager solve with an event pair around every phase
+    void profile(double* timings, double* counters) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        profiling_ = true;
+        span_used_ = 0;
+        launches_ = sor_launches_ = sor_launches_l0_ = 0;
+        PF_CUDA(cudaEventRecord(ev_[0], st_));
+        enqueue_solve();
+        set_phase(-1, 0);
+        PF_CUDA(cudaEventRecord(ev_[1], st_));
+        PF_CUDA(cudaStreamSynchronize(st_));
+        profiling_ = false;
+        for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
+        double sor_l0 = 0;
+        for (size_t i = 0; i < span_used_; i++) {
+            float ms = 0;
+            PF_CUDA(cudaEventElapsedTime(&ms, spans_[i].a, spans_[i].b));
+            timings[spans_[i].phase] += ms;
+            if (spans_[i].phase == PF_T_PHASE5_SOR && spans_[i].level == 0) sor_l0 += ms;
+        }
+        float tot = 0;
+        PF_CUDA(cudaEventElapsedTime(&tot, ev_[0], ev_[1]));
+        timings[PF_T_SOLVE] = tot;
+        timings[PF_T_TOTAL] = tot;
+        if (counters) {
+            double ps = 0;
+            for (int k = 0; k < nlev_; k++)
+                ps += (double)geo_[k].w * geo_[k].h * (P.n_outer + k) * P.n_inner * (P.n_sor + 3 * k);
+            counters[0] = (double)launches_;
+            counters[1] = (double)sor_launches_;
+            counters[2] = ps;
+            counters[3] = sor_l0;
+            counters[4] = (double)sor_launches_l0_;
+            counters[5] = (double)geo_[0].w * geo_[0].h * P.n_outer * P.n_inner * P.n_sor;
+            counters[6] = 0;
+            counters[7] = 0;
+        }
+    }
+
+    // ---- pieces reused by the single-stage entry points --------------------------------------
+    cudaStream_t stream() const { return st_; }
+
+  private:
+    // ------------------------------------------------------------------------------------------
+    Img<T> view(T* base, int w, int h, int c) const {
+        Img<T> v;
+        v.p = base; v.w = w; v.h = h; v.c = c;
+        v.pitch = pitch_for(w);
+        v.plane = plane_for(w, h);
+        return v;
+    }
+
+    void allocate() {
+        const size_t pl0 = plane_for(P.w, P.h);
+        const size_t in_elems = (size_t)P.h * P.w * P.c;
+        size_t total = 0;
+        total += 3 * Arena::need(in_elems, sizeof(double));              // in1, in2, warp out
+        total += 2 * Arena::need((size_t)P.h * P.w, sizeof(double));     // vx, vy out
+        for (int k = 0; k < nlev_; k++) total += 2 * Arena::need(plane_for(geo_[k].w, geo_[k].h) * P.c, sizeof(T));
+        total += 2 * Arena::need(pl0 * P.c, sizeof(T));                  // blur tmp, blur
+        total += 3 * Arena::need(pl0 * P.c, sizeof(T));                  // bicubic ix, iy, ixy
+        total += 10 * Arena::need(pl0 * fc_, sizeof(T));                 // f1 f2 wf s1 s2 tmp blend dx dy dt
+        total += 16 * Arena::need(pl0, sizeof(T));                       // scalar planes
+        total += Arena::need(64, sizeof(double)) * 2 + Arena::need(1, sizeof(BicubicTable));
+        arena_.reserve(total + 4096);
+        d_in1_ = arena_.take<double>(in_elems);
+        d_in2_ = arena_.take<double>(in_elems);
+        d_warp_ = arena_.take<double>(in_elems);
+        d_vx_ = arena_.take<double>((size_t)P.h * P.w);
+        d_vy_ = arena_.take<double>((size_t)P.h * P.w);
+        pyr1_.resize(nlev_);
+        pyr2_.resize(nlev_);
+        for (int k = 0; k < nlev_; k++) {
+            size_t n = plane_for(geo_[k].w, geo_[k].h) * P.c;
+            pyr1_[k] = view(arena_.take<T>(n), geo_[k].w, geo_[k].h, P.c);
+            pyr2_[k] = view(arena_.take<T>(n), geo_[k].w, geo_[k].h, P.c);
+        }
+        b_tmp_ = arena_.take<T>(pl0 * P.c);
+        b_out_ = arena_.take<T>(pl0 * P.c);
+        b_ix_ = arena_.take<T>(pl0 * P.c);
+        b_iy_ = arena_.take<T>(pl0 * P.c);
+        b_ixy_ = arena_.take<T>(pl0 * P.c);
+        T** fcb[] = {&f1_, &f2_, &wf_, &s1_, &s2_, &tmp_, &blend_, &imdx_, &imdy_, &imdt_};
+        for (T** b : fcb) *b = arena_.take<T>(pl0 * fc_);
+        T** sc[] = {&u_, &v_, &u2_, &v2_, &du_, &dv_, &du2_, &dv2_, &phi_, &dxy_, &iu_, &iv_, &bu_, &bv_, &dx2_, &dy2_};
+        for (T** b : sc) *b = arena_.take<T>(pl0);
+        d_lap_ = arena_.take<double>(64);
+        d_acc_ = arena_.take<double>(64);
+        d_tab_ = arena_.take<BicubicTable>(1);
+        BicubicTable tab = make_bicubic_table();
+        PF_CUDA(cudaMemcpy(d_tab_, &tab, sizeof(tab), cudaMemcpyHostToDevice));
+        PF_CUDA(cudaMemset(d_acc_, 0, 64 * sizeof(double)));
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void set_phase(int phase, int level) {
+        if (!profiling_) return;
+        if (span_used_ == spans_.size()) {
+            Span s{0, 0, nullptr, nullptr};
+            PF_CUDA(cudaEventCreate(&s.a));
+            PF_CUDA(cudaEventCreate(&s.b));
+            spans_.push_back(s);
+        }
+        if (open_) {
+            PF_CUDA(cudaEventRecord(spans_[span_used_ - 1].b, st_));
+            open_ = false;
+        }
+        if (phase >= 0) {
+            spans_[span_used_].phase = phase;
+            spans_[span_used_].level = level;
+            PF_CUDA(cudaEventRecord(spans_[span_used_].a, st_));
+            span_used_++;
+            open_ = true;
+        }
+    }
+
+    dim3 grid2(int w, int h, int z = 1) const { return dim3(ceil_div(w, 128), h, z); }
+
+    void filter_h(const Img<T>& s, const Img<T>& d, const Taps<T>& t) {
+        k_filter_h<T><<<grid2(s.w, s.h, s.c), 128, 0, st_>>>(s, d, t);
+        launches_++;
+    }
+    void filter_v(const Img<T>& s, const Img<T>& d, const Taps<T>& t) {
+        k_filter_v<T><<<grid2(s.w, s.h, s.c), 128, 0, st_>>>(s, d, t);
+        launches_++;
+    }
+
+    void run_solve() {
+        if (!use_graph_) {
+            enqueue_solve();
+            return;
+        }
+        if (!gexec_) {
+            PF_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_solve();
+            } catch (...) {
+                cudaGraph_t g = nullptr;
+                cudaStreamEndCapture(st_, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            PF_CUDA(cudaStreamEndCapture(st_, &graph_));
+            PF_CUDA(cudaGraphInstantiate(&gexec_, graph_, 0));
+        }
+        PF_CUDA(cudaGraphLaunch(gexec_, st_));
+    }
+
+    // ---- SOR dispatch: leaves the result in du_/dv_ (pointers may be swapped) ------------------
+    void run_sor(int w, int h, int pitch, int nsor, int level) {
+        SorArgs<T> a;
+        a.phi = phi_; a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
+        a.du = nullptr; a.dv = nullptr; a.du_in = nullptr; a.dv_in = nullptr;
+        a.w = w; a.h = h; a.pitch = pitch;
+        a.alpha = (T)P.alpha; a.omega = (T)1.8;
+        int n = sor_.run(a, du_, dv_, du2_, dv2_, nsor);
+        launches_ += n;
+        sor_launches_ += n;
+        if (level == 0) sor_launches_l0_ += n;
+    }
+
+    // ---- the whole solve on st_ ------------------------------------------------------------------
+    void enqueue_solve() {
+        const double d5raw[5] = {1.0 / 12, -8.0 / 12, 0.0 / 12, 8.0 / 12, -1.0 / 12};
+        const double g5raw[5] = {0.02, 0.11, 0.74, 0.11, 0.02};
+        const double d3raw[3] = {-0.5, 0, 0.5};
+        const Taps<T> d5 = make_taps<T>(d5raw, 2), g5 = make_taps<T>(g5raw, 2), d3 = make_taps<T>(d3raw, 1);
+        const T eps = (T)std::pow(0.001, 2);
+        T* du_entry = du_; T* dv_entry = dv_; T* du2_entry = du2_; T* dv2_entry = dv2_;
+        T* u_entry = u_; T* v_entry = v_; T* u2_entry = u2_; T* v2_entry = v2_;
+
+        // -- Construction: import + both pyramids (S/GaussianPyramid.cpp:79-108) --
+        set_phase(PF_T_CONSTRUCTION, 0);
+        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in1_, pyr1_[0]);
+        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in2_, pyr2_[0]);
+        launches_ += 2;
+        for (int side = 0; side < 2; side++) {
+            auto& pyr = side ? pyr2_ : pyr1_;
+            for (int i = 1; i < nlev_; i++) {
+                const Level& g = geo_[i];
+                const Img<T>& src = pyr[g.src];
+                Img<T> blurred = src;
+                if (g.half > 0) {   // half-width 0 is the identity filter (level 1, quirk Q2)
+                    Taps<T> gt = make_taps<T>(g.taps.data(), g.half);
+                    Img<T> tmp = view(b_tmp_, src.w, src.h, src.c);
+                    blurred = view(b_out_, src.w, src.h, src.c);
+                    filter_h(src, tmp, gt);
+                    filter_v(tmp, blurred, gt);
+                }
+                k_resize<T><<<grid2(g.w, g.h), 128, 0, st_>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
+                launches_++;
+            }
+        }
+        if (kF64 && lex_) {
+            double lap0[64];
+            for (int i = 0; i < 64; i++) lap0[i] = 0.02;   // S/OpticalFlow.cpp:773-775
+            PF_CUDA(cudaMemcpyAsync(d_lap_, lap0, sizeof(lap0), cudaMemcpyHostToDevice, st_));
+        }
+
+        int pw = 0, ph = 0;
+        for (int k = nlev_ - 1; k >= 0; k--) {
+            const int w = geo_[k].w, h = geo_[k].h, pitch = pitch_for(w);
+            const size_t plane_bytes = plane_for(w, h) * sizeof(T);
+            // -- Allocation: features, flow upsampling, warp (S/OpticalFlow.cpp:790-818) --
+            set_phase(PF_T_ALLOCATION, k);
+            Img<T> f1 = view(f1_, w, h, fc_), f2 = view(f2_, w, h, fc_), wf = view(wf_, w, h, fc_);
+            Img<T> s1 = view(s1_, w, h, fc_), s2 = view(s2_, w, h, fc_), tmp = view(tmp_, w, h, fc_);
+            Img<T> blend = view(blend_, w, h, fc_), imdx = view(imdx_, w, h, fc_);
+            Img<T> imdy = view(imdy_, w, h, fc_), imdt = view(imdt_, w, h, fc_);
+            if (P.c == 1 || P.c == 3) {
+                int swap = (k == 0 && P.col_type == 1) ? 1 : 0;
+                k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr1_[k], f1, d5, swap);
+                k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr2_[k], f2, d5, swap);
+            } else {
+                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr1_[k], f1);
+                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr2_[k], f2);
+            }
+            launches_ += 2;
+            if (k == nlev_ - 1) {
+                PF_CUDA(cudaMemsetAsync(u_, 0, plane_bytes, st_));
+                PF_CUDA(cudaMemsetAsync(v_, 0, plane_bytes, st_));
+                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(f2, wf);
+                launches_++;
+            } else {
+                Img<T> su = view(u_, pw, ph, 1), sv = view(v_, pw, ph, 1);
+                Img<T> du = view(u2_, w, h, 1), dv = view(v2_, w, h, 1);
+                double rx = (double)w / pw, ry = (double)h / ph;
+                T scale = (T)(1 / P.ratio);
+                k_resize<T><<<grid2(w, h), 128, 0, st_>>>(su, du, rx, ry, scale, 1);
+                k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
+                std::swap(u_, u2_);
+                std::swap(v_, v2_);
+                k_update_warp<T><<<grid2(w, h), 128, 0, st_>>>(f1, f2, wf, u_, v_, nullptr, nullptr, pitch);
+                launches_ += 3;
+            }
+            // Im1 is constant within a level: its smoothed copy is computed once instead of every
+            // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
+            set_phase(PF_T_PHASE1_GENERATE, k);
+            filter_h(f1, tmp, g5);
+            filter_v(tmp, s1, g5);
+
+            const int n_outer = P.n_outer + k, n_sor = P.n_sor + 3 * k;
+            for (int it = 0; it < n_outer; it++) {
+                // -- Phase1: getDxs (S/OpticalFlow.cpp:80-122) --
+                set_phase(PF_T_PHASE1_GENERATE, k);
+                filter_h(wf, tmp, g5);
+                filter_v(tmp, s2, g5);
+                k_blend_dt<T><<<grid2(w, h, fc_), 128, 0, st_>>>(s1, s2, blend, imdt);
+                launches_++;
+                filter_h(blend, imdx, d5);
+                filter_v(blend, imdy, d5);
+                for (int hh = 0; hh < P.n_inner; hh++) {
+                    // -- Phase2: flow derivatives + phi --
+                    set_phase(PF_T_PHASE2_DERIVS, k);
+                    const T* cdu = hh > 0 ? du_ : nullptr;
+                    const T* cdv = hh > 0 ? dv_ : nullptr;
+                    k_phi<T><<<grid2(w, h), 128, 0, st_>>>(u_, v_, cdu, cdv, phi_, w, h, pitch, eps);
+                    launches_++;
+                    // -- Phase3+4: psi, products, Laplacian, rhs --
+                    set_phase(PF_T_PHASE4_SYSTEM, k);
+                    AssembleArgs<T> a;
+                    a.imdx = imdx; a.imdy = imdy; a.imdt = imdt;
+                    a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
+                    a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+                    a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
+                    a.dx2 = nullptr; a.dy2 = nullptr;
+                    a.w = w; a.h = h; a.pitch = pitch;
+                    a.alpha = (T)P.alpha; a.omega = (T)1.8; a.eps = eps;
+                    k_assemble<T><<<grid2(w, h), 128, 0, st_>>>(a);
+                    launches_++;
+                    // -- Phase5: SOR --
+                    set_phase(PF_T_PHASE5_SOR, k);
+                    run_sor(w, h, pitch, n_sor, k);
+                }
+                // -- Phase6: update + warp (+ noise estimate in the parity mode) --
+                set_phase(PF_T_PHASE6_UPDATE, k);
+                k_update_warp<T><<<grid2(w, h), 128, 0, st_>>>(f1, f2, wf, u_, v_, du_, dv_, pitch);
+                launches_++;
+                if (kF64 && lex_) {
+                    k_noise_accum<T><<<dim3(std::min(8, ceil_div(w, 128)), std::min(h, 64), fc_), 128, 0, st_>>>(f1, wf, d_acc_);
+                    k_noise_final<<<1, 32, 0, st_>>>(d_acc_, d_lap_, fc_);
+                    launches_ += 2;
+                }
+            }
+            pw = w;
+            ph = h;
+        }
+        // -- PostProcessing: bicubic warp of the original frame + clamp; export the flow --
+        set_phase(PF_T_POST, 0);
+        {
+            const Img<T>& im1 = pyr1_[0];
+            const Img<T>& im2 = pyr2_[0];
+            Img<T> ix = view(b_ix_, P.w, P.h, P.c), iy = view(b_iy_, P.w, P.h, P.c), ixy = view(b_ixy_, P.w, P.h, P.c);
+            filter_h(im2, ix, d3);
+            filter_v(im2, iy, d3);
+            filter_v(ix, ixy, d3);
+            k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, d_warp_);
+            Img<T> uo = view(u_, P.w, P.h, 1), vo = view(v_, P.w, P.h, 1);
+            k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
+            k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(vo, d_vy_);
+            launches_ += 3;
+        }
+        PF_CHECK_LAUNCH();
+        // restore the pointer roles so that a captured graph and a later eager run agree
+        du_ = du_entry; dv_ = dv_entry; du2_ = du2_entry; dv2_ = dv2_entry;
+        u_ = u_entry; v_ = v_entry; u2_ = u2_entry; v2_ = v2_entry;
+    }
+
+  public:
+    Params P;
+
+  private:
+    bool lex_ = false, use_graph_ = true, profiling_ = false, open_ = false;
+    int nlev_ = 0, fc_ = 0;
+    SorRunner<T> sor_;
+    std::vector<Level> geo_;
+    Arena arena_;
+    cudaStream_t st_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph_ = nullptr;
+    cudaGraphExec_t gexec_ = nullptr;
+    std::vector<Span> spans_;
+    size_t span_used_ = 0;
+    long long launches_ = 0, sor_launches_ = 0, sor_launches_l0_ = 0;
+    double *d_in1_ = nullptr, *d_in2_ = nullptr, *d_warp_ = nullptr, *d_vx_ = nullptr, *d_vy_ = nullptr;
+    std::vector<Img<T>> pyr1_, pyr2_;
+    T *b_tmp_ = nullptr, *b_out_ = nullptr, *b_ix_ = nullptr, *b_iy_ = nullptr, *b_ixy_ = nullptr;
+    T *f1_ = nullptr, *f2_ = nullptr, *wf_ = nullptr, *s1_ = nullptr, *s2_ = nullptr, *tmp_ = nullptr;
+    T *blend_ = nullptr, *imdx_ = nullptr, *imdy_ = nullptr, *imdt_ = nullptr;
+    T *u_ = nullptr, *v_ = nullptr, *u2_ = nullptr, *v2_ = nullptr, *du_ = nullptr, *dv_ = nullptr;
+    T *du2_ = nullptr, *dv2_ = nullptr, *phi_ = nullptr, *dxy_ = nullptr, *iu_ = nullptr, *iv_ = nullptr;
+    T *bu_ = nullptr, *bv_ = nullptr, *dx2_ = nullptr, *dy2_ = nullptr;
+    double *d_lap_ = nullptr, *d_acc_ = nullptr;
+    BicubicTable* d_tab_ = nullptr;
+};
+
+}  // namespace pf

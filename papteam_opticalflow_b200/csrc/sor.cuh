@@ -1,0 +1,286 @@
+// SOR kernels (S/OpticalFlow.cpp:451-505).
+//
+//   k_sor_wavefront   lexicographic Gauss-Seidel, the reference's exact update order, run as a
+//                     pipelined anti-diagonal wavefront in one cooperative launch (parity mode).
+//   k_sor_rb_tile     red-black SOR with several sweeps fused per launch (temporal blocking),
+//                     coefficients and du/dv resident in registers (fast mode).
+//   k_sor_rb_half     one red-black half-sweep straight from global memory (cross-check only).
+//
+// Per pixel p=(i,j) the reference computes
+//     s1 = sum_nbr w du_nbr, s2 = sum_nbr w dv_nbr            w: left phi(p-1), right phi(p),
+//     s1 *= -alpha; s2 *= -alpha; s1 += dxy dv                   up phi(p-W), down phi(p)
+//     du = (1-omega) du + omega/(dx2 + .05 alpha + alpha sum_nbr w) * (bu - s1)
+//     s2 += dxy du(new);  dv likewise with dy2, bv
+// The omega/(...) factors iu, iv are loop invariant and come precomputed from k_assemble.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace pf {
+namespace cg = cooperative_groups;
+
+template <typename T>
+struct SorArgs {
+    const T *phi, *dxy, *iu, *iv, *bu, *bv;
+    T *du, *dv;              // in/out (wavefront, half-sweep) or output (tile kernel)
+    const T *du_in, *dv_in;  // tile kernel input (ping-pong: other CTAs read halos of the input)
+    int w, h, pitch;
+    T alpha, omega;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Parity mode.  Pixel (i,j) of sweep s needs (i,j-1),(i-1,j) of sweep s and (i,j+1),(i+1,j) of sweep
+// s-1, so anti-diagonal d=i+j of sweep s can run at step t = d + 2s: all nsor sweeps are pipelined
+// through (W+H-1) + 2(nsor-1) grid-synchronised steps instead of nsor*(W+H-1).  At any step the
+// written diagonals have the parity of t and the read neighbours the opposite parity, so the
+// in-place update is race free and reproduces the lexicographic order exactly.
+// du/dv are read with ld.global.cg (L2) because other SMs wrote them in the previous step.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_sor_wavefront(SorArgs<T> a, int nsor) {
+    cg::grid_group grid = cg::this_grid();
+    const int W = a.w, H = a.h, P = a.pitch;
+    const int nd = W + H - 1, L = min(W, H);
+    const int nsteps = nd + 2 * (nsor - 1);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const T one_m = (T)1 - a.omega;
+    const T nalpha = -a.alpha;
+    for (int t = 0; t < nsteps; t++) {
+        int s_hi = min(nsor - 1, t >> 1);
+        int over = t - (nd - 1);
+        int s_lo = over <= 0 ? 0 : (over + 1) >> 1;
+        long long work = (long long)(s_hi - s_lo + 1) * L;
+        for (long long idx = tid; idx < work; idx += nthreads) {
+            int s = s_lo + (int)(idx / L), m = (int)(idx % L);
+            int d = t - 2 * s;
+            int i = max(0, d - (W - 1)) + m;
+            if (i > min(H - 1, d)) continue;
+            int j = d - i;
+            size_t o = (size_t)i * P + j;
+            T s1 = 0, s2 = 0, wt;
+            if (j > 0)     { wt = a.phi[o - 1]; s1 += wt * __ldcg(a.du + o - 1); s2 += wt * __ldcg(a.dv + o - 1); }
+            if (j < W - 1) { wt = a.phi[o];     s1 += wt * __ldcg(a.du + o + 1); s2 += wt * __ldcg(a.dv + o + 1); }
+            if (i > 0)     { wt = a.phi[o - P]; s1 += wt * __ldcg(a.du + o - P); s2 += wt * __ldcg(a.dv + o - P); }
+            if (i < H - 1) { wt = a.phi[o];     s1 += wt * __ldcg(a.du + o + P); s2 += wt * __ldcg(a.dv + o + P); }
+            s1 *= nalpha;
+            s2 *= nalpha;
+            T du = __ldcg(a.du + o), dv = __ldcg(a.dv + o), dxy = a.dxy[o];
+            s1 += dxy * dv;
+            du = one_m * du + a.iu[o] * (a.bu[o] - s1);
+            s2 += dxy * du;
+            dv = one_m * dv + a.iv[o] * (a.bv[o] - s2);
+            a.du[o] = du;
+            a.dv[o] = dv;
+        }
+        grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-check: one colour of one red-black sweep, in place, one thread per updated pixel.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_sor_rb_half(SorArgs<T> a, int colour) {
+    int y = blockIdx.y;
+    int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((y + colour) & 1);
+    if (x >= a.w) return;
+    const int W = a.w, H = a.h, P = a.pitch;
+    size_t o = (size_t)y * P + x;
+    T s1 = 0, s2 = 0, wt;
+    if (x > 0)     { wt = a.phi[o - 1]; s1 += wt * a.du[o - 1]; s2 += wt * a.dv[o - 1]; }
+    if (x < W - 1) { wt = a.phi[o];     s1 += wt * a.du[o + 1]; s2 += wt * a.dv[o + 1]; }
+    if (y > 0)     { wt = a.phi[o - P]; s1 += wt * a.du[o - P]; s2 += wt * a.dv[o - P]; }
+    if (y < H - 1) { wt = a.phi[o];     s1 += wt * a.du[o + P]; s2 += wt * a.dv[o + P]; }
+    s1 *= -a.alpha;
+    s2 *= -a.alpha;
+    T du = a.du[o], dv = a.dv[o], dxy = a.dxy[o];
+    s1 += dxy * dv;
+    du = ((T)1 - a.omega) * du + a.iu[o] * (a.bu[o] - s1);
+    s2 += dxy * du;
+    dv = ((T)1 - a.omega) * dv + a.iv[o] * (a.bv[o] - s2);
+    a.du[o] = du;
+    a.dv[o] = dv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast mode: temporally blocked red-black SOR, register resident.
+//
+// A CTA owns a region of 64 x (NW*R) pixels: warp `wp` owns rows [wp*R, wp*R+R), lane `l` owns the
+// column pair {2l, 2l+1}.  All eight planes of the thread's 2 x R patch (alpha*phi, dxy, iu, iv, bu,
+// bv, du, dv) are loaded ONCE with 8-byte (16-byte in FP64) coalesced vector loads and stay in
+// registers for `nsw` fused sweeps; region origins and R are even, so the pixel updated in row r of
+// colour c is the compile-time column p = (r + c) & 1 and every lane does identical work.
+// Horizontal neighbours in the other lane travel by warp shuffle, vertical neighbours across warps
+// through one row pair of shared memory per warp and one __syncthreads per half-sweep.
+// Pixels outside the image are held at exactly zero with zero coefficients, so the reference's
+// "skip the missing neighbour" rule (S/OpticalFlow.cpp:468-495) needs no branches.
+// Regions overlap: a pixel at distance k from a region edge that is not an image edge is wrong after
+// k half-sweeps, so only the window 2*nsw inside such edges is written back, to a second buffer
+// (other CTAs still read the old values of their halos).
+// Algorithmic traffic per pixel-sweep drops from 10 words to about (8/eff + 2)/nsw, eff = window/region.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Vec2;
+template <> struct Vec2<float>  { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+
+constexpr int kSorRegionW = 64;
+
+template <typename T, int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_sor_rb_tile(SorArgs<T> a, int nsw, int step_x, int step_y) {
+    static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
+    typedef typename Vec2<T>::type V2;
+    constexpr int RH = NW * R;
+    __shared__ T ex[2][NW][2][kSorRegionW];  // [du|dv][warp][top|bottom][x]
+
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int W = a.w, H = a.h, P = a.pitch;
+    const int HL = 2 * nsw;
+    const int rx0 = blockIdx.x * step_x, ry0 = blockIdx.y * step_y;  // even by construction
+    const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
+
+    T w[R][2], dxy[R][2], iu[R][2], iv[R][2], bu[R][2], bv[R][2], du[R][2], dv[R][2];
+    T wl[R], wu[2];
+
+    auto ld2 = [&](const T* base, int y, T& v0, T& v1) {
+        if (y < H && xa < W) {
+            V2 t = *reinterpret_cast<const V2*>(base + (size_t)y * P + xa);
+            v0 = t.x;
+            v1 = (xa + 1 < W) ? t.y : (T)0;
+        } else {
+            v0 = 0;
+            v1 = 0;
+        }
+    };
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int y = ya + r;
+        ld2(a.phi, y, w[r][0], w[r][1]);
+        ld2(a.dxy, y, dxy[r][0], dxy[r][1]);
+        ld2(a.iu, y, iu[r][0], iu[r][1]);
+        ld2(a.iv, y, iv[r][0], iv[r][1]);
+        ld2(a.bu, y, bu[r][0], bu[r][1]);
+        ld2(a.bv, y, bv[r][0], bv[r][1]);
+        ld2(a.du_in, y, du[r][0], du[r][1]);
+        ld2(a.dv_in, y, dv[r][0], dv[r][1]);
+    }
+    // weight of the row above the patch (phi at y-1) -- zero outside the image
+    {
+        int y = ya - 1;
+        if (y >= 0) ld2(a.phi, y, wu[0], wu[1]);
+        else { wu[0] = 0; wu[1] = 0; }
+        wu[0] *= a.alpha;
+        wu[1] *= a.alpha;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        w[r][0] *= a.alpha;
+        w[r][1] *= a.alpha;
+        // weight towards the left lane's odd column, phi(xa-1, y): zero for lane 0 when rx0 == 0
+        T t = __shfl_up_sync(0xffffffffu, w[r][1], 1);
+        if (lane == 0) {
+            int y = ya + r;
+            t = (xa > 0 && y < H) ? a.alpha * a.phi[(size_t)y * P + xa - 1] : (T)0;
+        }
+        wl[r] = t;
+    }
+    const T one_m = (T)1 - a.omega;
+
+    auto publish = [&]() {
+        *reinterpret_cast<V2*>(&ex[0][wp][0][2 * lane]) = V2{du[0][0], du[0][1]};
+        *reinterpret_cast<V2*>(&ex[1][wp][0][2 * lane]) = V2{dv[0][0], dv[0][1]};
+        *reinterpret_cast<V2*>(&ex[0][wp][1][2 * lane]) = V2{du[R - 1][0], du[R - 1][1]};
+        *reinterpret_cast<V2*>(&ex[1][wp][1][2 * lane]) = V2{dv[R - 1][0], dv[R - 1][1]};
+    };
+    publish();
+    __syncthreads();
+
+    for (int s = 0; s < nsw; s++) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            // vertical neighbours owned by other warps (zero at the region's top / bottom edge)
+            const int p_top = c & 1, p_bot = (R - 1 + c) & 1;
+            T up_du = 0, up_dv = 0, dn_du = 0, dn_dv = 0;
+            if (wp > 0) {
+                up_du = ex[0][wp - 1][1][2 * lane + p_top];
+                up_dv = ex[1][wp - 1][1][2 * lane + p_top];
+            }
+            if (wp < NW - 1) {
+                dn_du = ex[0][wp + 1][0][2 * lane + p_bot];
+                dn_dv = ex[1][wp + 1][0][2 * lane + p_bot];
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int p = (r + c) & 1;
+                // horizontal neighbours: one is the thread's own other column, one lives in a lane
+                T lw, ldu, ldv, rdu, rdv;
+                if (p == 1) {
+                    lw = w[r][0]; ldu = du[r][0]; ldv = dv[r][0];
+                    rdu = __shfl_down_sync(0xffffffffu, du[r][0], 1);
+                    rdv = __shfl_down_sync(0xffffffffu, dv[r][0], 1);
+                    if (lane == 31) { rdu = 0; rdv = 0; }
+                } else {
+                    lw = wl[r];
+                    ldu = __shfl_up_sync(0xffffffffu, du[r][1], 1);
+                    ldv = __shfl_up_sync(0xffffffffu, dv[r][1], 1);
+                    if (lane == 0) { ldu = 0; ldv = 0; }
+                    rdu = du[r][1]; rdv = dv[r][1];
+                }
+                T uw, udu, udv, ddu, ddv;
+                if (r > 0) { uw = w[r - 1][p]; udu = du[r - 1][p]; udv = dv[r - 1][p]; }
+                else       { uw = wu[p];       udu = up_du;        udv = up_dv; }
+                if (r < R - 1) { ddu = du[r + 1][p]; ddv = dv[r + 1][p]; }
+                else           { ddu = dn_du;        ddv = dn_dv; }
+                const T cw = w[r][p];
+                T s1 = bu[r][p] + lw * ldu + cw * rdu + uw * udu + cw * ddu;
+                T s2 = bv[r][p] + lw * ldv + cw * rdv + uw * udv + cw * ddv;
+                s1 -= dxy[r][p] * dv[r][p];
+                T nu = one_m * du[r][p] + iu[r][p] * s1;
+                s2 -= dxy[r][p] * nu;
+                T nv = one_m * dv[r][p] + iv[r][p] * s2;
+                du[r][p] = nu;
+                dv[r][p] = nv;
+            }
+            __syncthreads();   // everyone has consumed the previous exchange rows
+            publish();
+            __syncthreads();
+        }
+    }
+
+    // write back the window that is still exact
+    const int ox_lo = blockIdx.x > 0 ? rx0 + HL : 0;
+    const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
+    const int oy_lo = blockIdx.y > 0 ? ry0 + HL : 0;
+    const int oy_hi = (ry0 + RH >= H) ? H : ry0 + RH - HL;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int y = ya + r;
+        if (y < oy_lo || y >= oy_hi) continue;
+        bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
+        size_t o = (size_t)y * P + xa;
+        if (v0 && v1) {
+            *reinterpret_cast<V2*>(a.du + o) = V2{du[r][0], du[r][1]};
+            *reinterpret_cast<V2*>(a.dv + o) = V2{dv[r][0], dv[r][1]};
+        } else if (v0) {
+            a.du[o] = du[r][0];
+            a.dv[o] = dv[r][0];
+        } else if (v1) {
+            a.du[o + 1] = du[r][1];
+            a.dv[o + 1] = dv[r][1];
+        }
+    }
+}
+
+// Tiling of an image dimension of size n by regions of size `region` whose exact window shrinks by
+// `halo` on every side that is not an image edge.  Region origins are step*k.
+struct SorTiling {
+    int ntiles, step;
+};
+inline SorTiling sor_tiling(int n, int region, int halo) {
+    if (n <= region) return {1, region};
+    int step = region - 2 * halo;
+    if (step < 2) return {0, 0};
+    return {ceil_div(n - region, step) + 1, step};
+}
+
+}  // namespace pf

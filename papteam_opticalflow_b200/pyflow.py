@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference's Cython module `pyflow` (Par/pyflow.pyx:31-70).
+
+    coarse2fine_flow(Im1, Im2, pyramidLevels[, nCores])                      -> (timing, vx, vy, warpI2)
+        the fork's call shape (Par/pyflow.pyx:31-33; serial flavour Ser/pyflow.pyx:31-33 has no nCores);
+        alpha=0.012 ratio=0.75 7/1/30 are the fork's hard-coded constants (S/OpticalFlow.cpp:747-751).
+    coarse2fine_flow(im1, im2, alpha, ratio, minWidth, nOuterFPIterations,
+                     nInnerFPIterations, nSORIterations, colType)               -> (u, v, im2W)
+        upstream pyflow's call shape, the one BASELINE.json's north_star names (parameter list at
+        Par/pyflow.pyx:36-41).
+
+Inputs are float64, C-contiguous, (h, w, c) arrays in [0,1], gray passed as (h, w, 1); outputs are
+freshly allocated float64 arrays -- exactly the reference's contract.  Keyword-only extras:
+    mode    'fp32_redblack' (fast, default) | 'fp64_wavefront' (matches the reference to <=1e-6)
+            | 'fp64_redblack' | 'fp32_wavefront'      (env PYFLOW_B200_MODE overrides the default)
+    device  CUDA device index (default 0)
+    profile True: run eagerly with CUDA events per phase and fill every timing key
+"""
+import collections
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import PyflowB200Error, check, dp  # noqa: F401
+
+MODES = {"fp64_wavefront": 0, "fp32_redblack": 1, "fp64_redblack": 2, "fp32_wavefront": 3}
+_FORK_DEFAULTS = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30, colType=0)
+# reference timing-map keys (S/OpticalFlow.cpp:850-860) in PF_T_* order, then the GPU-only legs
+_TIMING_KEYS = ["Total C++ Execution", "Construction", "Allocation", "Phase1_Generate",
+                "Phase2_Derivatives", "Phase3_PsiData", "Phase4_LinearSystem", "Phase5_SOR",
+                "Phase6_Update", "PostProcessing", "H2D", "D2H", "Solve"]
+
+
+def _mode_id(mode):
+    if mode is None:
+        mode = os.environ.get("PYFLOW_B200_MODE", "fp32_redblack")
+    if isinstance(mode, str):
+        if mode not in MODES:
+            raise ValueError("unknown mode %r (expected one of %s)" % (mode, sorted(MODES)))
+        return MODES[mode]
+    if mode in MODES.values():
+        return int(mode)
+    raise ValueError("unknown mode %r" % (mode,))
+
+
+def _check_image(name, a):
+    """Same acceptance rules as Cython's `np.ndarray[double, ndim=3, mode="c"] X not None`."""
+    if a is None:
+        raise TypeError("Argument '%s' must not be None" % name)
+    if not isinstance(a, np.ndarray):
+        raise TypeError("Argument '%s' has incorrect type (expected numpy.ndarray, got %s)" % (name, type(a).__name__))
+    if a.ndim != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % a.ndim)
+    if a.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'double' but got '%s'" % a.dtype.name)
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("ndarray is not C-contiguous")
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(dp)
+
+
+class FlowPlan(object):
+    """Device arena + captured CUDA graph for one image shape / parameter set (pf_plan_*)."""
+
+    def __init__(self, h, w, c, alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30,
+                 colType=0, levels=0, mode=None, device=0):
+        self.shape = (int(h), int(w), int(c))
+        self.mode = _mode_id(mode)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        self._lock = threading.Lock()
+        check(_lib.lib().pf_plan_create(C.byref(self._h), h, w, c, float(alpha), float(ratio), int(minWidth),
+                                        int(levels), int(nOuter), int(nInner), int(nSOR), int(colType),
+                                        self.mode, self.device))
+        self.levels = _lib.lib().pf_plan_levels(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().pf_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _outputs(self):
+        h, w, c = self.shape
+        return np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))
+
+    def _check_pair(self, im1, im2):
+        _check_image("Im1", im1)
+        _check_image("Im2", im2)
+        if im1.shape != self.shape or im2.shape != self.shape:
+            raise ValueError("image shapes %s / %s do not match the plan's %s" % (im1.shape, im2.shape, self.shape))
+
+    def execute(self, im1, im2, out=None):
+        """H2D + solve + D2H.  Returns (timings_ms ndarray, vx, vy, warpI2)."""
+        self._check_pair(im1, im2)
+        vx, vy, wi = out if out is not None else self._outputs()
+        t = np.zeros(_lib.PF_NUM_TIMINGS)
+        with self._lock:
+            check(_lib.lib().pf_plan_execute(self._h, _ptr(vx), _ptr(vy), _ptr(wi), _ptr(im1), _ptr(im2), _ptr(t)))
+        return t, vx, vy, wi
+
+    def upload(self, im1, im2):
+        self._check_pair(im1, im2)
+        with self._lock:
+            check(_lib.lib().pf_plan_upload(self._h, _ptr(im1), _ptr(im2)))
+
+    def solve(self, repeats=1):
+        """Device-only solve on the resident inputs; returns total milliseconds (CUDA events)."""
+        ms = C.c_double()
+        with self._lock:
+            check(_lib.lib().pf_plan_solve(self._h, int(repeats), C.byref(ms)))
+        return ms.value
+
+    def download(self, out=None):
+        vx, vy, wi = out if out is not None else self._outputs()
+        with self._lock:
+            check(_lib.lib().pf_plan_download(self._h, _ptr(vx), _ptr(vy), _ptr(wi)))
+        return vx, vy, wi
+
+    def profile(self):
+        """One eager solve with events around every phase: (timings_ms, counters)."""
+        t = np.zeros(_lib.PF_NUM_TIMINGS)
+        cnt = np.zeros(8)
+        with self._lock:
+            check(_lib.lib().pf_plan_profile(self._h, _ptr(t), _ptr(cnt)))
+        return t, cnt
+
+
+_plans = collections.OrderedDict()
+_plans_lock = threading.Lock()
+_MAX_PLANS = 4
+
+
+def _get_plan(key, **kw):
+    with _plans_lock:
+        p = _plans.pop(key, None)
+        if p is None:
+            p = FlowPlan(**kw)
+            while len(_plans) >= _MAX_PLANS:
+                _, old = _plans.popitem(last=False)
+                old.close()
+        _plans[key] = p
+        return p
+
+
+def _timing_dict(t_ms):
+    # the reference stringifies seconds with std::to_string (6 decimals)
+    return {k: "%.6f" % (t_ms[i] / 1000.0) for i, k in enumerate(_TIMING_KEYS)}
+
+
+def coarse2fine_flow(Im1, Im2, *args, **kwargs):
+    mode = kwargs.pop("mode", None)
+    device = kwargs.pop("device", 0)
+    profile = kwargs.pop("profile", False)
+    if kwargs:
+        raise TypeError("coarse2fine_flow() got unexpected keyword arguments %s" % sorted(kwargs))
+    n = len(args)
+    if n in (1, 2):
+        fork = True
+        levels = int(args[0])
+        if n == 2:
+            int(args[1])                      # nCores: accepted, type-checked, ignored
+        if levels < 1:
+            raise ValueError("pyramidLevels must be >= 1")
+        p = dict(_FORK_DEFAULTS)
+    elif n == 7:
+        fork = False
+        levels = 0
+        p = dict(alpha=float(args[0]), ratio=float(args[1]), minWidth=int(args[2]), nOuter=int(args[3]),
+                 nInner=int(args[4]), nSOR=int(args[5]), colType=int(args[6]))
+    else:
+        raise TypeError("coarse2fine_flow() takes (Im1, Im2, pyramidLevels[, nCores]) or (im1, im2, alpha, ratio, "
+                        "minWidth, nOuterFPIterations, nInnerFPIterations, nSORIterations, colType); got %d positional "
+                        "arguments" % (n + 2))
+    _check_image("Im1", Im1)
+    _check_image("Im2", Im2)
+    if Im1.shape != Im2.shape:
+        raise ValueError("Im1 and Im2 must have the same shape, got %s and %s" % (Im1.shape, Im2.shape))
+    h, w, c = Im1.shape
+    mid = _mode_id(mode)
+    key = (h, w, c, tuple(sorted(p.items())), levels, mid, int(device))
+    plan = _get_plan(key, h=h, w=w, c=c, levels=levels, mode=mid, device=device, **p)
+    t, vx, vy, wi = plan.execute(Im1, Im2)
+    if fork:
+        if profile:
+            tp, _ = plan.profile()
+            for i in range(1, 10):
+                t[i] = tp[i]
+        return _timing_dict(t), vx, vy, wi
+    return vx, vy, wi
+
+
+def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,
+                           nInnerFPIterations=1, nSORIterations=30, colType=0, levels=0, mode=None,
+                           devices=None):
+    """Solve a list of independent (im1, im2) pairs, pair p on devices[p % len(devices)], no
+    collective.  Returns ([(u, v, im2W), ...], wall_seconds)."""
+    L = _lib.lib()
+    if devices is None:
+        devices = list(range(max(1, L.pf_device_count())))
+    n = len(pairs)
+    if n == 0:
+        return [], 0.0
+    for a, b in pairs:
+        _check_image("Im1", a)
+        _check_image("Im2", b)
+        if a.shape != pairs[0][0].shape or b.shape != a.shape:
+            raise ValueError("all images of a batch must share one shape")
+    h, w, c = pairs[0][0].shape
+    outs = [(np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))) for _ in range(n)]
+    arr = lambda xs: (dp * n)(*[_ptr(x) for x in xs])  # noqa: E731
+    dev = (C.c_int * len(devices))(*devices)
+    secs = C.c_double()
+    check(L.pf_batch_flow(n, arr([o[0] for o in outs]), arr([o[1] for o in outs]), arr([o[2] for o in outs]),
+                          arr([p[0] for p in pairs]), arr([p[1] for p in pairs]), float(alpha), float(ratio),
+                          int(minWidth), int(levels), int(nOuterFPIterations), int(nInnerFPIterations),
+                          int(nSORIterations), int(colType), h, w, c, _mode_id(mode), dev, len(devices),
+                          C.byref(secs)))
+    return outs, secs.value

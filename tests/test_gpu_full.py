@@ -1,0 +1,169 @@
+"""End-to-end parity of the CUDA path through the drop-in `pyflow` module (C ABI underneath).
+
+Parity mode (FP64 lexicographic wavefront): max |flow difference| <= 1e-6 vs the reference
+(BASELINE.json north_star); in practice the results are bit-identical.
+Fast mode (FP32 red-black): mean endpoint error <= 0.02 px, max <= 0.5 px vs the reference flow;
+im2W reported as mean / p99.9 (max cannot hold: warps switch discontinuously at the image border,
+SURVEY.md F6)."""
+import numpy as np
+import pytest
+
+import pyflow
+from conftest import golden, load_frame, synthetic_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def epe(u, v, gu, gv):
+    return np.hypot(u - gu, v - gv)
+
+
+def test_config1_240_parity_mode_vs_reference_golden():
+    g = golden("hcm240_L8.npz")
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    t, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 8, 4, mode="fp64_wavefront")
+    assert np.abs(vx - g["vx"]).max() <= 1e-6 and np.abs(vy - g["vy"]).max() <= 1e-6
+    assert np.abs(wi - g["warpI2"]).max() <= 1e-6
+    assert isinstance(t, dict) and float(t["Total C++ Execution"]) > 0
+    # upstream call shape, minWidth=20 <=> 8 levels
+    u, v, w2 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp64_wavefront")
+    assert np.array_equal(u, vx) and np.array_equal(v, vy) and np.array_equal(w2, wi)
+
+
+def test_config1_240_fast_mode():
+    for name, i in (("hcm240_L8.npz", 1), ("hcm240_p30_31_L8.npz", 30)):
+        g = golden(name)
+        a, b = load_frame(240, i), load_frame(240, i + 1)
+        u, v, w2 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+        e = epe(u, v, g["vx"], g["vy"])
+        assert e.mean() <= 0.02 and e.max() <= 0.5, (e.mean(), e.max())
+        d = np.abs(w2 - g["warpI2"])
+        assert d.mean() <= 1e-3 and np.quantile(d, 0.999) <= 2e-2
+
+
+def test_gray_nondefault_params_two_inner_iterations():
+    g = golden("hcm240_gray_params.npz")
+    kw = (float(g["alpha"]), float(g["ratio"]), int(g["minWidth"]), int(g["nOuter"]), int(g["nInner"]),
+          int(g["nSOR"]), int(g["colType"]))
+    a, b = np.ascontiguousarray(g["im1"]), np.ascontiguousarray(g["im2"])
+    u, v, w2 = pyflow.coarse2fine_flow(a, b, *kw, mode="fp64_wavefront")
+    assert np.abs(u - g["vx"]).max() <= 1e-6 and np.abs(v - g["vy"]).max() <= 1e-6
+    assert np.abs(w2 - g["warpI2"]).max() <= 1e-6
+    u, v, w2 = pyflow.coarse2fine_flow(a, b, *kw, mode="fp32_redblack")
+    e = epe(u, v, g["vx"], g["vy"])
+    assert e.mean() <= 0.02 and e.max() <= 0.5, (e.mean(), e.max())
+
+
+@pytest.mark.parametrize("w,lv,name", [(480, 11, "hcm480_L11_s4.npz"), (960, 13, "hcm960_L13_s8.npz")])
+def test_config2_parity_mode_subsampled_golden(w, lv, name):
+    g = golden(name)
+    s = int(g["stride"])
+    a, b = load_frame(w, 1), load_frame(w, 2)
+    _, vx, vy, wi = pyflow.coarse2fine_flow(a, b, lv, mode="fp64_wavefront")
+    assert np.abs(vx[::s, ::s] - g["vx"]).max() <= 1e-6 and np.abs(vy[::s, ::s] - g["vy"]).max() <= 1e-6
+    assert np.abs(wi[::s, ::s] - g["warpI2"]).max() <= 1e-6
+    # full-array checksums recorded from the reference run
+    assert np.allclose([vx.sum(), vy.sum(), wi.sum()], g["sums"], rtol=0, atol=1e-5)
+    assert np.allclose([vx.min(), vx.max(), vy.min(), vy.max()], g["minmax"], rtol=0, atol=1e-6)
+
+
+def test_config3_1920_fast_mode_subsampled_golden():
+    g = golden("hcm1920_L15_s8.npz")
+    s = int(g["stride"])
+    a, b = load_frame(1920, 1), load_frame(1920, 2)
+    u, v, w2 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    e = epe(u[::s, ::s], v[::s, ::s], g["vx"], g["vy"])
+    d = np.abs(w2[::s, ::s] - g["warpI2"])
+    print("1920 fast mode: EPE mean %.5f p99 %.5f max %.5f | im2W mean %.2e p99.9 %.2e max %.3f frac>1e-3 %.4f%%"
+          % (e.mean(), np.quantile(e, 0.99), e.max(), d.mean(), np.quantile(d, 0.999), d.max(), 100 * (d > 1e-3).mean()))
+    assert e.mean() <= 0.02 and e.max() <= 0.5
+    assert d.mean() <= 1e-3
+
+
+def test_config3_1920_parity_mode_subsampled_golden():
+    g = golden("hcm1920_L15_s8.npz")
+    s = int(g["stride"])
+    a, b = load_frame(1920, 1), load_frame(1920, 2)
+    _, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 15, mode="fp64_wavefront")
+    assert np.abs(vx[::s, ::s] - g["vx"]).max() <= 1e-6 and np.abs(vy[::s, ::s] - g["vy"]).max() <= 1e-6
+    assert np.abs(wi[::s, ::s] - g["warpI2"]).max() <= 1e-6
+    assert np.allclose([vx.sum(), vy.sum(), wi.sum()], g["sums"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["identical", "gray", "rgb_coltype1", "bad_ratio", "tiny", "odd_sizes", "one_level"])
+def test_edge_cases_both_modes_vs_oracle(oracle_mod, case):
+    im1, im2 = synthetic_pair(48, 72, 3, seed=5, shift=(2.25, 1.5))
+    kw = [0.012, 0.75, 20, 3, 1, 10, 0]
+    if case == "identical":
+        im2 = im1.copy()
+    elif case == "gray":
+        im1, im2 = np.ascontiguousarray(im1[..., :1]), np.ascontiguousarray(im2[..., :1]); kw[6] = 1
+    elif case == "rgb_coltype1":
+        kw[6] = 1
+    elif case == "bad_ratio":
+        kw[1] = 0.3
+    elif case == "tiny":
+        im1, im2 = synthetic_pair(9, 13, 3, seed=2, shift=(0.5, 0.25)); kw[2] = 6
+    elif case == "odd_sizes":
+        im1, im2 = synthetic_pair(67, 131, 3, seed=3, shift=(1.0, -2.0))
+    elif case == "one_level":
+        kw[2] = 60
+    if oracle_mod.levels_from_min_width(im1.shape[1], kw[1], kw[2]) < 1:
+        with pytest.raises(Exception):
+            pyflow.coarse2fine_flow(im1, im2, *kw, mode="fp64_wavefront")
+        return
+    ox, oy, ow = oracle_mod.coarse2fine_flow(im1, im2, *kw)
+    u, v, w2 = pyflow.coarse2fine_flow(im1, im2, *kw, mode="fp64_wavefront")
+    assert np.abs(u - ox).max() <= 1e-6 and np.abs(v - oy).max() <= 1e-6 and np.abs(w2 - ow).max() <= 1e-6
+    u, v, w2 = pyflow.coarse2fine_flow(im1, im2, *kw, mode="fp32_redblack")
+    e = epe(u, v, ox, oy)
+    assert e.mean() <= 0.02 and e.max() <= 0.5, (case, e.mean(), e.max())
+    if case == "identical":
+        assert np.abs(u).max() == 0 and np.abs(v).max() == 0
+
+
+def test_ordering_vs_rounding_budget(oracle_mod):
+    """fp64_redblack isolates the ordering error, fp32_wavefront the rounding error."""
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    lx, ly, _ = oracle_mod.coarse2fine_flow(a, b, levels=8)
+    rx, ry, _ = oracle_mod.coarse2fine_flow(a, b, levels=8, order=oracle_mod.REDBLACK)
+    _, u, v, _ = pyflow.coarse2fine_flow(a, b, 8, mode="fp64_redblack")
+    assert epe(u, v, rx, ry).max() <= 1e-6          # same ordering as the oracle's red-black variant
+    _, u, v, _ = pyflow.coarse2fine_flow(a, b, 8, mode="fp32_wavefront")
+    e = epe(u, v, lx, ly)
+    assert e.mean() <= 0.01 and e.max() <= 0.5
+
+
+def test_api_errors_and_timing_keys():
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    with pytest.raises(ValueError):
+        pyflow.coarse2fine_flow(a.astype(np.float32), b, 8)
+    with pytest.raises(ValueError):
+        pyflow.coarse2fine_flow(a[..., 0], b[..., 0], 8)
+    with pytest.raises(TypeError):
+        pyflow.coarse2fine_flow(None, b, 8)
+    with pytest.raises(TypeError):
+        pyflow.coarse2fine_flow(a, b, 1, 2, 3)
+    with pytest.raises(ValueError):
+        pyflow.coarse2fine_flow(a, b[:, :100].copy(), 8)
+    t, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 8, 2, profile=True)
+    for k in ("Total C++ Execution", "Construction", "Allocation", "Phase1_Generate", "Phase2_Derivatives",
+              "Phase3_PsiData", "Phase4_LinearSystem", "Phase5_SOR", "Phase6_Update", "PostProcessing"):
+        assert k in t and float(t[k]) >= 0
+    assert float(t["Phase5_SOR"]) > 0
+    assert vx.shape == (135, 240) and wi.shape == (135, 240, 3) and vx.dtype == np.float64
+
+
+def test_plan_resident_path_and_batch():
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    plan = pyflow.FlowPlan(135, 240, 3, mode="fp32_redblack")
+    _, vx, vy, wi = plan.execute(a, b)
+    plan.upload(a, b)
+    ms = plan.solve(3)
+    x2, y2, w2 = plan.download()
+    assert ms > 0 and np.array_equal(vx, x2) and np.array_equal(vy, y2) and np.array_equal(wi, w2)
+    t, cnt = plan.profile()
+    assert cnt[0] > 0 and cnt[2] == pytest.approx(2.047e7, rel=0.01)   # BASELINE.md pixel-sweep table
+    outs, secs = pyflow.coarse2fine_flow_batch([(a, b), (b, a), (a, b)], mode="fp32_redblack")
+    assert np.array_equal(outs[0][0], vx) and np.array_equal(outs[2][1], vy) and secs > 0
+    plan.close()
