@@ -104,6 +104,13 @@ int pf_plan_download(pf_plan* plan, double* vx, double* vy, double* warpI2);
  * [2] SOR pixel-sweeps, [3] SOR ms at level 0, [4] SOR launches at level 0,
  * [5] pixel-sweeps at level 0. */
 int pf_plan_profile(pf_plan* plan, double* timings, double* counters);
+/* `repeats` solves on each of `nplans` plans of ONE device, all streams running concurrently
+ * (pairs are independent): total GPU milliseconds between a start event every stream waits on and a
+ * stop event that waits on every stream.  This is how a batch of resident pairs is timed. */
+int pf_multi_solve(pf_plan* const* plans, int nplans, int repeats, double* ms_total);
+/* Per-level phase times (ms) of the last pf_plan_profile call: out[level][PF_NUM_TIMINGS];
+ * returns the number of levels written. */
+int pf_plan_level_timings(const pf_plan* plan, double* out, int max_levels);
 
 /* ---- batches: N independent frame pairs sharded over devices, no collective ---
  * pair p runs on devices[p % ndevices]; im1/im2/vx/vy/warpI2 are arrays of N host pointers. */

@@ -52,6 +52,8 @@ def lib():
         "pf_plan_solve": (i, [v, i, dp]),
         "pf_plan_download": (i, [v, dp, dp, dp]),
         "pf_plan_profile": (i, [v, dp, dp]),
+        "pf_plan_level_timings": (i, [v, dp, i]),
+        "pf_multi_solve": (i, [C.POINTER(v), i, i, dp]),
         "pf_batch_flow": (i, [i, dpp, dpp, dpp, dpp, dpp, d, d, i, i, i, i, i, i, i, i, i, i, ip, i, dp]),
         "pf_stage_pyramid": (i, [dp, dp, i, i, i, d, i, i, i]),
         "pf_stage_im2feature": (i, [dp, dp, i, i, i, i, i, i]),

@@ -187,6 +187,55 @@ int pf_plan_profile(pf_plan* plan, double* timings, double* counters) {
     });
 }
 
+int pf_multi_solve(pf_plan* const* plans, int nplans, int repeats, double* ms_total) {
+    return guarded([&]() -> int {
+        if (!plans || nplans < 1 || repeats < 1) return fail(PF_EINVAL, "bad argument");
+        for (int i = 0; i < nplans; i++) {
+            if (!plans[i]) return fail(PF_EINVAL, "NULL plan");
+            if (plans[i]->impl->device() != plans[0]->impl->device()) return fail(PF_EINVAL, "plans must share one device");
+        }
+        PF_CUDA(cudaSetDevice(plans[0]->impl->device()));
+        cudaStream_t s0 = plans[0]->impl->stream();
+        cudaEvent_t start, stop;
+        std::vector<cudaEvent_t> done((size_t)nplans);
+        PF_CUDA(cudaEventCreate(&start));
+        PF_CUDA(cudaEventCreate(&stop));
+        for (auto& e : done) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        auto cleanup = [&]() {
+            cudaEventDestroy(start); cudaEventDestroy(stop);
+            for (auto& e : done) cudaEventDestroy(e);
+        };
+        try {
+            PF_CUDA(cudaDeviceSynchronize());
+            // the start event is recorded on plan 0's stream; every other stream waits for it, and
+            // plan 0's stream waits for every other stream before the stop event is recorded
+            PF_CUDA(cudaEventRecord(start, s0));
+            for (int i = 1; i < nplans; i++) PF_CUDA(cudaStreamWaitEvent(plans[i]->impl->stream(), start, 0));
+            for (int r = 0; r < repeats; r++)
+                for (int i = 0; i < nplans; i++) plans[i]->impl->solve_async(1);
+            for (int i = 1; i < nplans; i++) {
+                PF_CUDA(cudaEventRecord(done[(size_t)i], plans[i]->impl->stream()));
+                PF_CUDA(cudaStreamWaitEvent(s0, done[(size_t)i], 0));
+            }
+            PF_CUDA(cudaEventRecord(stop, s0));
+            PF_CUDA(cudaStreamSynchronize(s0));
+            float ms = 0;
+            PF_CUDA(cudaEventElapsedTime(&ms, start, stop));
+            if (ms_total) *ms_total = ms;
+        } catch (...) {
+            cleanup();
+            throw;
+        }
+        cleanup();
+        return PF_OK;
+    });
+}
+
+int pf_plan_level_timings(const pf_plan* plan, double* out, int max_levels) {
+    if (!plan || !out || max_levels < 1) return fail(PF_EINVAL, "bad argument");
+    return plan->impl->level_timings(out, max_levels);
+}
+
 int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im1,
                         const double* im2, double alpha, double ratio, int minWidth, int nOuter,
                         int nInner, int nSOR, int colType, int h, int w, int c, int mode, int device,
@@ -228,24 +277,40 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
         if (r) return r;
     }
     auto t0 = std::chrono::steady_clock::now();
+    // PF_BATCH_STREAMS workers (plan + stream each) per device pull pairs from one queue, so the
+    // H2D / solve / D2H legs of different pairs overlap and the latency-bound coarse levels of one
+    // pair hide behind the bandwidth-bound fine levels of another.
+    const char* env = getenv("PF_BATCH_STREAMS");
+    int per_dev = env ? atoi(env) : 3;
+    if (per_dev < 1) per_dev = 1;
+    if (mode_is_lex(mode)) per_dev = 1;   // cooperative launches do not overlap usefully
+    const int nworkers = std::min(std::max(npairs, 1), ndevices * per_dev);
     std::vector<std::thread> workers;
-    std::vector<int> status((size_t)ndevices, PF_OK);
-    std::vector<std::string> messages((size_t)ndevices);
-    for (int d = 0; d < ndevices; d++) {
-        workers.emplace_back([&, d]() {
+    std::vector<int> status((size_t)nworkers, PF_OK);
+    std::vector<std::string> messages((size_t)nworkers);
+    std::vector<std::atomic<int>> next((size_t)ndevices);
+    for (auto& n : next) n.store(0);
+    for (int wk = 0; wk < nworkers; wk++) {
+        workers.emplace_back([&, wk]() {
+            const int d = wk % ndevices;
             pf_plan* pl = nullptr;
             int r = pf_plan_create(&pl, h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[d]);
-            for (int p = d; r == PF_OK && p < npairs; p += ndevices)
+            // pair p belongs to device p % ndevices; workers of one device share its queue
+            while (r == PF_OK) {
+                int k = next[(size_t)d].fetch_add(1);
+                int p = d + k * ndevices;
+                if (p >= npairs) break;
                 r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], nullptr);
-            if (r) messages[(size_t)d] = g_err;
+            }
+            if (r) messages[(size_t)wk] = g_err;
             if (pl) pf_plan_destroy(pl);
-            status[(size_t)d] = r;
+            status[(size_t)wk] = r;
         });
     }
     for (auto& t : workers) t.join();
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    for (int d = 0; d < ndevices; d++)
-        if (status[(size_t)d]) return fail(status[(size_t)d], messages[(size_t)d]);
+    for (int wk = 0; wk < nworkers; wk++)
+        if (status[(size_t)wk]) return fail(status[(size_t)wk], messages[(size_t)wk]);
     return PF_OK;
 }
 

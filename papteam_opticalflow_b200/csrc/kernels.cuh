@@ -416,4 +416,216 @@ inline BicubicTable make_bicubic_table() {
     return t;
 }
 
+
+// =============================================================================================
+// Fused outer-iteration front end: getDxs + phi + linear-system assembly in ONE kernel.
+//
+// Replaces nine launches (2x smooth h/v of the warped image, blend/dt, 2x derivative, phi, assemble)
+// and their ~90 words/pixel of plane traffic by a single pass that reads the warped features (with a
+// 4-pixel halo), the per-level smoothed Im1 (2-pixel halo), u and v (1-pixel halo) and writes the six
+// coefficient planes: ~21 words/pixel.  One CTA owns a TX x TY output tile and walks the feature
+// channels; per channel the raw tile is staged in shared memory, smoothed horizontally then
+// vertically ([.02,.11,.74,.11,.02], S/OpticalFlow.cpp:84-90), blended .4/.6 with the smoothed Im1
+// (:91-93), differentiated with [1,-8,0,8,-1]/12 (:95-96) and folded into the five psi-weighted sums
+// (:377-427) held in registers.  Every shared-memory read goes through the CLAMPED image coordinate,
+// which is exactly the replicate-border rule of S/ImageProcessing.h:259-279/350-369, and every sum
+// keeps the reference's term order, so the FP64 instantiation is bit-identical to the unfused path.
+// =============================================================================================
+template <typename T>
+struct FusedArgs {
+    Img<T> s1, wf;                 // smoothed Im1 features (per level), warped Im2 features
+    const T *u, *v, *du, *dv;      // du/dv: current increments (nullptr = zero, first inner iteration)
+    const double* lap;             // per-channel noise scale guard (nullptr = always on)
+    T *phi, *dxy, *iu, *iv, *bu, *bv;
+    int w, h, pitch;               // pitch of the scalar planes
+    T alpha, omega, eps;
+    Taps<T> g5, d5;
+};
+
+template <typename T, int TX, int TY>
+__global__ void __launch_bounds__(256) k_fused_assemble(FusedArgs<T> a) {
+    constexpr int NT = 256, PPT = TX * TY / NT;       // pixels per thread
+    constexpr int RW = TX + 8, RHt = TY + 8;          // raw tile   (halo 4)
+    constexpr int HW = TX + 4;                        // h-smoothed (halo 2 in x, 4 in y)
+    constexpr int BW = TX + 4, BH = TY + 4;           // blend tile (halo 2)
+    constexpr int UW = TX + 2, UH = TY + 2;           // u/v tiles  (halo 1)
+    constexpr int PW = TX + 1, PH = TY + 1;           // phi tile   (halo 1 left/up)
+    static_assert(TX * TY % NT == 0, "tile must be a multiple of the block");
+    static_assert(2 * UW * UH <= RW * RHt + HW * RHt, "u/v tiles alias the raw + hs tiles");
+    static_assert(PW * PH <= BW * BH, "phi tile aliases the blend tile");
+    __shared__ T sm_raw[RHt * RW + RHt * HW];
+    __shared__ T sm_bl[BH * BW];
+    __shared__ T sm_dt[TY * TX];
+    T* raw = sm_raw;
+    T* hs = sm_raw + RHt * RW;
+    T* bl = sm_bl;
+
+    const int W = a.w, H = a.h;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.x;
+    const int C = a.wf.c;
+
+    T sxy[PPT], sx2[PPT], sy2[PPT], stx[PPT], sty[PPT], cdu[PPT], cdv[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        sxy[k] = sx2[k] = sy2[k] = stx[k] = sty[k] = 0;
+        int p = tid + k * NT, px = x0 + p % TX, py = y0 + p / TX;
+        cdu[k] = cdv[k] = 0;
+        if (a.du && px < W && py < H) {
+            cdu[k] = a.du[(size_t)py * a.pitch + px];
+            cdv[k] = a.dv[(size_t)py * a.pitch + px];
+        }
+    }
+
+    for (int c = 0; c < C; c++) {
+        const T* wfc = a.wf.ch(c);
+        const T* s1c = a.s1.ch(c);
+        const bool active = !(a.lap && a.lap[c] < 1e-20);   // S/OpticalFlow.cpp:399-400
+        // 1. stage the raw tile, replicate borders through clamped coordinates
+        for (int i = tid; i < RHt * RW; i += NT) {
+            int ry = i / RW, rx = i - ry * RW;
+            int Y = clampi(y0 - 4 + ry, H), X = clampi(x0 - 4 + rx, W);
+            raw[i] = wfc[(size_t)Y * a.wf.pitch + X];
+        }
+        __syncthreads();
+        // 2. horizontal smoothing for columns x0-2 .. x0+TX+1, all staged rows
+        for (int i = tid; i < RHt * HW; i += NT) {
+            int ry = i / HW, hx = i - ry * HW;
+            int X = clampi(x0 - 2 + hx, W);
+            T acc = 0;
+#pragma unroll
+            for (int l = -2; l <= 2; l++) acc += raw[ry * RW + (clampi(X + l, W) - (x0 - 4))] * a.g5.v[l + 2];
+            hs[i] = acc;
+        }
+        __syncthreads();
+        // 3. vertical smoothing, blend with the smoothed Im1, temporal difference at the centre
+        for (int i = tid; i < BH * BW; i += NT) {
+            int by = i / BW, bx = i - by * BW;
+            int Y = clampi(y0 - 2 + by, H), X = clampi(x0 - 2 + bx, W);
+            T acc = 0;
+#pragma unroll
+            for (int m = -2; m <= 2; m++) acc += hs[(clampi(Y + m, H) - (y0 - 4)) * HW + bx] * a.g5.v[m + 2];
+            T s1v = s1c[(size_t)Y * a.s1.pitch + X];
+            T t = s1v * (T)0.4;
+            bl[i] = t + acc * (T)0.6;
+            int cx = bx - 2, cy = by - 2;
+            if (cx >= 0 && cx < TX && cy >= 0 && cy < TY) sm_dt[cy * TX + cx] = acc - s1v;
+        }
+        __syncthreads();
+        // 4. derivatives of the blend at the centre pixels, psi-weighted products
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            int p = tid + k * NT, cx = p % TX, cy = p / TX;
+            int X = x0 + cx, Y = y0 + cy;
+            if (X < W && Y < H) {
+                T ix = 0, iy = 0;
+#pragma unroll
+                for (int l = -2; l <= 2; l++) ix += bl[(cy + 2) * BW + (clampi(X + l, W) - (x0 - 2))] * a.d5.v[l + 2];
+#pragma unroll
+                for (int l = -2; l <= 2; l++) iy += bl[(clampi(Y + l, H) - (y0 - 2)) * BW + (cx + 2)] * a.d5.v[l + 2];
+                T it = sm_dt[cy * TX + cx];
+                T psi = 0;
+                if (active) {
+                    T t = it + ix * cdu[k] + iy * cdv[k];
+                    t *= t;
+                    psi = (T)1 / ((T)2 * sqrt(t + a.eps));
+                }
+                T px = psi * ix, py = psi * iy;
+                sxy[k] += px * iy;
+                sx2[k] += px * ix;
+                sy2[k] += py * iy;
+                stx[k] += px * it;
+                sty[k] += py * it;
+            }
+        }
+        __syncthreads();
+    }
+
+    // 5. u+du, v+dv tiles with a 1-pixel halo -> phi on the tile plus its left/up halo; then the
+    //    same two tiles are reloaded with plain u, v for the Laplacian (which acts on u, not u+du:
+    //    S/OpticalFlow.cpp:437-438).  With du == nullptr both are the same and nothing is reloaded.
+    T* tu = sm_raw;
+    T* tv = tu + UW * UH;
+    T* tphi = sm_bl;
+    for (int i = tid; i < UW * UH; i += NT) {
+        int uy = i / UW, ux = i - uy * UW;
+        int Y = clampi(y0 - 1 + uy, H), X = clampi(x0 - 1 + ux, W);
+        size_t o = (size_t)Y * a.pitch + X;
+        T uv = a.u[o], vv = a.v[o];
+        tu[i] = a.du ? uv + a.du[o] : uv;
+        tv[i] = a.dv ? vv + a.dv[o] : vv;
+    }
+    __syncthreads();
+    for (int i = tid; i < PW * PH; i += NT) {
+        int py = i / PW, px = i - py * PW;
+        int X = x0 - 1 + px, Y = y0 - 1 + py;          // image coordinate of this phi entry
+        T val = 0;
+        if (X >= 0 && X < W && Y >= 0 && Y < H) {
+            int ui = py * UW + px;                      // same coordinate in the u tiles
+            T u0 = tu[ui], v0 = tv[ui];
+            T ux = 0, uy = 0, vx = 0, vy = 0;
+            if (X < W - 1) { ux = tu[ui + 1] - u0; vx = tv[ui + 1] - v0; }
+            if (Y < H - 1) { uy = tu[ui + UW] - u0; vy = tv[ui + UW] - v0; }
+            T t = ux * ux + uy * uy + vx * vx + vy * vy;
+            val = (T)0.5 / sqrt(t + a.eps);
+        }
+        tphi[i] = val;
+    }
+    __syncthreads();
+    if (a.du) {
+        for (int i = tid; i < UW * UH; i += NT) {
+            int uy = i / UW, ux = i - uy * UW;
+            int Y = clampi(y0 - 1 + uy, H), X = clampi(x0 - 1 + ux, W);
+            size_t o = (size_t)Y * a.pitch + X;
+            tu[i] = a.u[o];
+            tv[i] = a.v[o];
+        }
+        __syncthreads();
+    }
+    // 6. Laplacian (fork quirk F3), right-hand sides, inverse diagonals
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        int p = tid + k * NT, cx = p % TX, cy = p / TX;
+        int X = x0 + cx, Y = y0 + cy;
+        if (X >= W || Y >= H) continue;
+        const int pi = (cy + 1) * PW + (cx + 1), ui = (cy + 1) * UW + (cx + 1);
+        const T ph = tphi[pi];
+        T lu = 0, lv = 0, cf = 0;
+        if (X < W - 1) {
+            lu -= (tu[ui + 1] - tu[ui]) * ph;
+            lv -= (tv[ui + 1] - tv[ui]) * ph;
+            if (X > 0) {
+                lu += (tu[ui] - tu[ui - 1]) * tphi[pi - 1];
+                lv += (tv[ui] - tv[ui - 1]) * tphi[pi - 1];
+            }
+        }
+        if (Y < H - 1) {
+            lu -= (tu[ui + UW] - tu[ui]) * ph;
+            lv -= (tv[ui + UW] - tv[ui]) * ph;
+            if (Y > 0) {
+                lu += (tu[ui] - tu[ui - UW]) * tphi[pi - PW];
+                lv += (tv[ui] - tv[ui - UW]) * tphi[pi - PW];
+            }
+        }
+        if (X > 0) cf += tphi[pi - 1];
+        if (X < W - 1) cf += ph;
+        if (Y > 0) cf += tphi[pi - PW];
+        if (Y < H - 1) cf += ph;
+        cf *= a.alpha;
+        T a_xy = sxy[k], a_x2 = sx2[k], a_y2 = sy2[k], a_tx = stx[k], a_ty = sty[k];
+        if (C > 1) {
+            T n = (T)C;
+            a_xy /= n; a_x2 /= n; a_y2 /= n; a_tx /= n; a_ty /= n;
+        }
+        T reg = a.alpha * (T)0.05;
+        size_t o = (size_t)Y * a.pitch + X;
+        a.phi[o] = ph;
+        a.dxy[o] = a_xy;
+        a.iu[o] = a.omega / (a_x2 + reg + cf);
+        a.iv[o] = a.omega / (a_y2 + reg + cf);
+        a.bu[o] = -a_tx - a.alpha * lu;
+        a.bv[o] = -a_ty - a.alpha * lv;
+    }
+}
+
 }  // namespace pf

@@ -25,6 +25,10 @@ struct PlanBase {
     virtual void execute(double* vx, double* vy, double* warp, const double* im1,
                          const double* im2, double* timings) = 0;
     virtual void profile(double* timings, double* counters) = 0;
+    virtual int level_timings(double* out, int max_levels) const = 0;
+    virtual void solve_async(int repeats) = 0;   // enqueue only
+    virtual cudaStream_t stream() const = 0;
+    virtual int device() const = 0;
 };
 
 // ---- simple bump allocator over one cudaMalloc ---------------------------------------------------
@@ -127,9 +131,12 @@ struct SorRunner {
     int run(SorArgs<T> a, T*& du, T*& dv, T*& du2, T*& dv2, int nsor) {
         const int w = a.w, h = a.h;
         size_t bytes = plane_for(w, h) * sizeof(T);
-        PF_CUDA(cudaMemsetAsync(du, 0, bytes, st));
-        PF_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
         int launches = 0;
+        if (lex || simple_rb || nsor == 0) {
+            PF_CUDA(cudaMemsetAsync(du, 0, bytes, st));
+            PF_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
+        }
+        if (nsor == 0) return 0;
         if (lex) {
             a.du = du; a.dv = dv; a.du_in = nullptr; a.dv_in = nullptr;
             long long work = (long long)nsor * std::min(w, h);
@@ -153,7 +160,7 @@ struct SorRunner {
             int nsw = std::min(fuse, nsor - done);
             SorTiling tx = sor_tiling(w, kSorRegionW, 2 * nsw), ty = sor_tiling(h, kRegionH, 2 * nsw);
             if (tx.ntiles == 0 || ty.ntiles == 0) throw Error(PF_EINVAL, "SOR tiling failed");
-            a.du_in = du; a.dv_in = dv; a.du = du2; a.dv = dv2;
+            a.du_in = done ? du : nullptr; a.dv_in = done ? dv : nullptr; a.du = du2; a.dv = dv2;
             k_sor_rb_tile<T, kR, kNW><<<dim3(tx.ntiles, ty.ntiles), kNW * 32, 0, st>>>(a, nsw, tx.step, ty.step);
             launches++;
             std::swap(du, du2);
@@ -181,6 +188,8 @@ class Plan : public PlanBase {
         if (fc_ > 16) throw Error(PF_EUNSUPPORTED, "more than 16 channels");
         const char* e = getenv("PF_NO_GRAPH");
         use_graph_ = !(e && atoi(e)) && !lex_;
+        e = getenv("PF_UNFUSED");
+        fused_ = !(e && atoi(e));
         PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
         allocate();
@@ -268,10 +277,12 @@ class Plan : public PlanBase {
         profiling_ = false;
         for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
         double sor_l0 = 0;
+        level_ms_.assign((size_t)nlev_ * PF_NUM_TIMINGS, 0.0);
         for (size_t i = 0; i < span_used_; i++) {
             float ms = 0;
             PF_CUDA(cudaEventElapsedTime(&ms, spans_[i].a, spans_[i].b));
             timings[spans_[i].phase] += ms;
+            level_ms_[(size_t)spans_[i].level * PF_NUM_TIMINGS + spans_[i].phase] += ms;
             if (spans_[i].phase == PF_T_PHASE5_SOR && spans_[i].level == 0) sor_l0 += ms;
         }
         float tot = 0;
@@ -293,8 +304,21 @@ class Plan : public PlanBase {
         }
     }
 
-    // ---- pieces reused by the single-stage entry points --------------------------------------
-    cudaStream_t stream() const { return st_; }
+    void solve_async(int repeats) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        for (int i = 0; i < repeats; i++) run_solve();
+    }
+    cudaStream_t stream() const override { return st_; }
+    int device() const override { return P.device; }
+
+    // per-level phase times of the last profile() call: out[level][PF_NUM_TIMINGS]
+    int level_timings(double* out, int max_levels) const override {
+        int n = std::min(max_levels, nlev_);
+        if (level_ms_.empty()) return 0;
+        for (int k = 0; k < n; k++)
+            for (int j = 0; j < PF_NUM_TIMINGS; j++) out[k * PF_NUM_TIMINGS + j] = level_ms_[(size_t)k * PF_NUM_TIMINGS + j];
+        return n;
+    }
 
   private:
     // ------------------------------------------------------------------------------------------
@@ -497,33 +521,50 @@ class Plan : public PlanBase {
 
             const int n_outer = P.n_outer + k, n_sor = P.n_sor + 3 * k;
             for (int it = 0; it < n_outer; it++) {
-                // -- Phase1: getDxs (S/OpticalFlow.cpp:80-122) --
-                set_phase(PF_T_PHASE1_GENERATE, k);
-                filter_h(wf, tmp, g5);
-                filter_v(tmp, s2, g5);
-                k_blend_dt<T><<<grid2(w, h, fc_), 128, 0, st_>>>(s1, s2, blend, imdt);
-                launches_++;
-                filter_h(blend, imdx, d5);
-                filter_v(blend, imdy, d5);
+                if (!fused_) {
+                    // -- Phase1: getDxs (S/OpticalFlow.cpp:80-122), one kernel per reference step --
+                    set_phase(PF_T_PHASE1_GENERATE, k);
+                    filter_h(wf, tmp, g5);
+                    filter_v(tmp, s2, g5);
+                    k_blend_dt<T><<<grid2(w, h, fc_), 128, 0, st_>>>(s1, s2, blend, imdt);
+                    launches_++;
+                    filter_h(blend, imdx, d5);
+                    filter_v(blend, imdy, d5);
+                }
                 for (int hh = 0; hh < P.n_inner; hh++) {
-                    // -- Phase2: flow derivatives + phi --
-                    set_phase(PF_T_PHASE2_DERIVS, k);
                     const T* cdu = hh > 0 ? du_ : nullptr;
                     const T* cdv = hh > 0 ? dv_ : nullptr;
-                    k_phi<T><<<grid2(w, h), 128, 0, st_>>>(u_, v_, cdu, cdv, phi_, w, h, pitch, eps);
-                    launches_++;
-                    // -- Phase3+4: psi, products, Laplacian, rhs --
-                    set_phase(PF_T_PHASE4_SYSTEM, k);
-                    AssembleArgs<T> a;
-                    a.imdx = imdx; a.imdy = imdy; a.imdt = imdt;
-                    a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
-                    a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
-                    a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
-                    a.dx2 = nullptr; a.dy2 = nullptr;
-                    a.w = w; a.h = h; a.pitch = pitch;
-                    a.alpha = (T)P.alpha; a.omega = (T)1.8; a.eps = eps;
-                    k_assemble<T><<<grid2(w, h), 128, 0, st_>>>(a);
-                    launches_++;
+                    if (fused_) {
+                        // -- Phases 1-4 in one pass over the level (k_fused_assemble) --
+                        set_phase(PF_T_PHASE4_SYSTEM, k);
+                        FusedArgs<T> fa;
+                        fa.s1 = s1; fa.wf = wf;
+                        fa.u = u_; fa.v = v_; fa.du = cdu; fa.dv = cdv;
+                        fa.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+                        fa.phi = phi_; fa.dxy = dxy_; fa.iu = iu_; fa.iv = iv_; fa.bu = bu_; fa.bv = bv_;
+                        fa.w = w; fa.h = h; fa.pitch = pitch;
+                        fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = eps;
+                        fa.g5 = g5; fa.d5 = d5;
+                        k_fused_assemble<T, kFTX, kFTY><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), 256, 0, st_>>>(fa);
+                        launches_++;
+                    } else {
+                        // -- Phase2: flow derivatives + phi --
+                        set_phase(PF_T_PHASE2_DERIVS, k);
+                        k_phi<T><<<grid2(w, h), 128, 0, st_>>>(u_, v_, cdu, cdv, phi_, w, h, pitch, eps);
+                        launches_++;
+                        // -- Phase3+4: psi, products, Laplacian, rhs --
+                        set_phase(PF_T_PHASE4_SYSTEM, k);
+                        AssembleArgs<T> a;
+                        a.imdx = imdx; a.imdy = imdy; a.imdt = imdt;
+                        a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
+                        a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+                        a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
+                        a.dx2 = nullptr; a.dy2 = nullptr;
+                        a.w = w; a.h = h; a.pitch = pitch;
+                        a.alpha = (T)P.alpha; a.omega = (T)1.8; a.eps = eps;
+                        k_assemble<T><<<grid2(w, h), 128, 0, st_>>>(a);
+                        launches_++;
+                    }
                     // -- Phase5: SOR --
                     set_phase(PF_T_PHASE5_SOR, k);
                     run_sor(w, h, pitch, n_sor, k);
@@ -566,7 +607,8 @@ class Plan : public PlanBase {
     Params P;
 
   private:
-    bool lex_ = false, use_graph_ = true, profiling_ = false, open_ = false;
+    static constexpr int kFTX = 64, kFTY = 16;   // output tile of k_fused_assemble
+    bool lex_ = false, use_graph_ = true, fused_ = true, profiling_ = false, open_ = false;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;
     std::vector<Level> geo_;
@@ -576,6 +618,7 @@ class Plan : public PlanBase {
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t gexec_ = nullptr;
     std::vector<Span> spans_;
+    std::vector<double> level_ms_;
     size_t span_used_ = 0;
     long long launches_ = 0, sor_launches_ = 0, sor_launches_l0_ = 0;
     double *d_in1_ = nullptr, *d_in2_ = nullptr, *d_warp_ = nullptr, *d_vx_ = nullptr, *d_vy_ = nullptr;

@@ -161,8 +161,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_sor_rb_tile(SorArgs<T> a, int ns
         ld2(a.iv, y, iv[r][0], iv[r][1]);
         ld2(a.bu, y, bu[r][0], bu[r][1]);
         ld2(a.bv, y, bv[r][0], bv[r][1]);
-        ld2(a.du_in, y, du[r][0], du[r][1]);
-        ld2(a.dv_in, y, dv[r][0], dv[r][1]);
+        if (a.du_in) {                       // nullptr: the solve starts from du = dv = 0
+            ld2(a.du_in, y, du[r][0], du[r][1]);
+            ld2(a.dv_in, y, dv[r][0], dv[r][1]);
+        } else {
+            du[r][0] = du[r][1] = dv[r][0] = dv[r][1] = 0;
+        }
     }
     // weight of the row above the patch (phi at y-1) -- zero outside the image
     {

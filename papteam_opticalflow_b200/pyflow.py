@@ -131,6 +131,22 @@ class FlowPlan(object):
             check(_lib.lib().pf_plan_profile(self._h, _ptr(t), _ptr(cnt)))
         return t, cnt
 
+    def level_timings(self):
+        """(levels, PF_NUM_TIMINGS) array of per-level phase milliseconds from the last profile()."""
+        out = np.zeros((self.levels, _lib.PF_NUM_TIMINGS))
+        with self._lock:
+            check(_lib.lib().pf_plan_level_timings(self._h, _ptr(out), self.levels))
+        return out
+
+
+def multi_solve(plans, repeats=1):
+    """Concurrent device-only solves of several resident plans (one stream each) on one device;
+    returns total milliseconds from CUDA events (pf_multi_solve)."""
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    ms = C.c_double()
+    check(_lib.lib().pf_multi_solve(arr, len(plans), int(repeats), C.byref(ms)))
+    return ms.value
+
 
 _plans = collections.OrderedDict()
 _plans_lock = threading.Lock()
