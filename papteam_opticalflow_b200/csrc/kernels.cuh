@@ -442,100 +442,176 @@ struct FusedArgs {
     Taps<T> g5, d5;
 };
 
-template <typename T, int TX, int TY>
-__global__ void __launch_bounds__(256) k_fused_assemble(FusedArgs<T> a) {
-    constexpr int NT = 256, PPT = TX * TY / NT;       // pixels per thread
+// psi = 1 / (2 sqrt(t + eps)).  FP64 keeps the reference's expression; FP32 uses the hardware
+// reciprocal square root (2 ulp), far below the single-precision noise of the products it scales.
+__device__ __forceinline__ double psi_of(double t, double eps) { return 1.0 / (2.0 * sqrt(t + eps)); }
+__device__ __forceinline__ float psi_of(float t, float eps) { return 0.5f * rsqrtf(t + eps); }
+
+// Thread layout (256 threads, 8 warps): tile rows are dealt to warps and columns to lanes when
+// staging (coalesced, conflict free, no div/mod); for the vertical filters, the derivative stage
+// and the final stage thread t owns column t%64 and the contiguous row segment t/64, so the
+// vertical 5-tap windows slide through registers (1.4 shared loads per output instead of 5).
+// INTERIOR tiles (tile + 4-pixel halo inside the image) skip every clamp and border test.
+template <typename T, int TX, int TY, int SEG, bool INTERIOR>
+__device__ __forceinline__ void fused_assemble_body(const FusedArgs<T>& a, T* sm_raw, T* sm_bl, T* sm_dt) {
+    constexpr int NT = TX * SEG, NWARP = NT / 32;
+    constexpr int PPT = TY / SEG;                     // centre pixels per thread (rows of its segment)
     constexpr int RW = TX + 8, RHt = TY + 8;          // raw tile   (halo 4)
     constexpr int HW = TX + 4;                        // h-smoothed (halo 2 in x, 4 in y)
     constexpr int BW = TX + 4, BH = TY + 4;           // blend tile (halo 2)
+    constexpr int BSEG = (BH + SEG - 1) / SEG;        // blend rows per segment (last one may be short)
     constexpr int UW = TX + 2, UH = TY + 2;           // u/v tiles  (halo 1)
     constexpr int PW = TX + 1, PH = TY + 1;           // phi tile   (halo 1 left/up)
-    static_assert(TX * TY % NT == 0, "tile must be a multiple of the block");
-    static_assert(2 * UW * UH <= RW * RHt + HW * RHt, "u/v tiles alias the raw + hs tiles");
-    static_assert(PW * PH <= BW * BH, "phi tile aliases the blend tile");
-    __shared__ T sm_raw[RHt * RW + RHt * HW];
-    __shared__ T sm_bl[BH * BW];
-    __shared__ T sm_dt[TY * TX];
+    static_assert(TX == 64, "thread layout assumes 64-wide tiles");
+    static_assert(TY % SEG == 0, "tile height must split into SEG segments");
     T* raw = sm_raw;
     T* hs = sm_raw + RHt * RW;
     T* bl = sm_bl;
 
     const int W = a.w, H = a.h;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col = tid & (TX - 1), seg = tid / TX;
     const int C = a.wf.c;
+    auto cx_ = [&](int X) { return INTERIOR ? X : clampi(X, W); };
+    auto cy_ = [&](int Y) { return INTERIOR ? Y : clampi(Y, H); };
 
+    // centre pixels of this thread: (x0+col, y0 + seg*PPT + k)
+    const int PX = x0 + col;
+    const bool col_ok = INTERIOR || PX < W;
     T sxy[PPT], sx2[PPT], sy2[PPT], stx[PPT], sty[PPT], cdu[PPT], cdv[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
         sxy[k] = sx2[k] = sy2[k] = stx[k] = sty[k] = 0;
-        int p = tid + k * NT, px = x0 + p % TX, py = y0 + p / TX;
         cdu[k] = cdv[k] = 0;
-        if (a.du && px < W && py < H) {
-            cdu[k] = a.du[(size_t)py * a.pitch + px];
-            cdv[k] = a.dv[(size_t)py * a.pitch + px];
+        int PY = y0 + seg * PPT + k;
+        if (a.du && col_ok && (INTERIOR || PY < H)) {
+            cdu[k] = a.du[(size_t)PY * a.pitch + PX];
+            cdv[k] = a.dv[(size_t)PY * a.pitch + PX];
         }
     }
+    const T g0 = a.g5.v[0], g1 = a.g5.v[1], g2 = a.g5.v[2], g3 = a.g5.v[3], g4 = a.g5.v[4];
+    const T d0 = a.d5.v[0], d1 = a.d5.v[1], d3 = a.d5.v[3], d4 = a.d5.v[4];   // centre tap is 0
 
     for (int c = 0; c < C; c++) {
         const T* wfc = a.wf.ch(c);
         const T* s1c = a.s1.ch(c);
         const bool active = !(a.lap && a.lap[c] < 1e-20);   // S/OpticalFlow.cpp:399-400
-        // 1. stage the raw tile, replicate borders through clamped coordinates
-        for (int i = tid; i < RHt * RW; i += NT) {
-            int ry = i / RW, rx = i - ry * RW;
-            int Y = clampi(y0 - 4 + ry, H), X = clampi(x0 - 4 + rx, W);
-            raw[i] = wfc[(size_t)Y * a.wf.pitch + X];
+        // 1. stage the raw tile: warp per row, lanes across the row
+        for (int ry = warp; ry < RHt; ry += NWARP) {
+            const T* row = wfc + (size_t)cy_(y0 - 4 + ry) * a.wf.pitch;
+            for (int rx = lane; rx < RW; rx += 32) raw[ry * RW + rx] = row[cx_(x0 - 4 + rx)];
         }
         __syncthreads();
-        // 2. horizontal smoothing for columns x0-2 .. x0+TX+1, all staged rows
-        for (int i = tid; i < RHt * HW; i += NT) {
-            int ry = i / HW, hx = i - ry * HW;
-            int X = clampi(x0 - 2 + hx, W);
-            T acc = 0;
-#pragma unroll
-            for (int l = -2; l <= 2; l++) acc += raw[ry * RW + (clampi(X + l, W) - (x0 - 4))] * a.g5.v[l + 2];
-            hs[i] = acc;
-        }
-        __syncthreads();
-        // 3. vertical smoothing, blend with the smoothed Im1, temporal difference at the centre
-        for (int i = tid; i < BH * BW; i += NT) {
-            int by = i / BW, bx = i - by * BW;
-            int Y = clampi(y0 - 2 + by, H), X = clampi(x0 - 2 + bx, W);
-            T acc = 0;
-#pragma unroll
-            for (int m = -2; m <= 2; m++) acc += hs[(clampi(Y + m, H) - (y0 - 4)) * HW + bx] * a.g5.v[m + 2];
-            T s1v = s1c[(size_t)Y * a.s1.pitch + X];
-            T t = s1v * (T)0.4;
-            bl[i] = t + acc * (T)0.6;
-            int cx = bx - 2, cy = by - 2;
-            if (cx >= 0 && cx < TX && cy >= 0 && cy < TY) sm_dt[cy * TX + cx] = acc - s1v;
-        }
-        __syncthreads();
-        // 4. derivatives of the blend at the centre pixels, psi-weighted products
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-            int p = tid + k * NT, cx = p % TX, cy = p / TX;
-            int X = x0 + cx, Y = y0 + cy;
-            if (X < W && Y < H) {
-                T ix = 0, iy = 0;
-#pragma unroll
-                for (int l = -2; l <= 2; l++) ix += bl[(cy + 2) * BW + (clampi(X + l, W) - (x0 - 2))] * a.d5.v[l + 2];
-#pragma unroll
-                for (int l = -2; l <= 2; l++) iy += bl[(clampi(Y + l, H) - (y0 - 2)) * BW + (cx + 2)] * a.d5.v[l + 2];
-                T it = sm_dt[cy * TX + cx];
-                T psi = 0;
-                if (active) {
-                    T t = it + ix * cdu[k] + iy * cdv[k];
-                    t *= t;
-                    psi = (T)1 / ((T)2 * sqrt(t + a.eps));
+        // 2. horizontal smoothing for columns x0-2 .. x0+TX+1 of every staged row
+        for (int ry = warp; ry < RHt; ry += NWARP) {
+            const T* r = raw + ry * RW;
+            for (int hx = lane; hx < HW; hx += 32) {
+                T acc = 0;
+                if (INTERIOR) {
+                    acc += r[hx] * g0; acc += r[hx + 1] * g1; acc += r[hx + 2] * g2;
+                    acc += r[hx + 3] * g3; acc += r[hx + 4] * g4;
+                } else {
+                    int X = clampi(x0 - 2 + hx, W), o = x0 - 4;
+                    acc += r[clampi(X - 2, W) - o] * g0; acc += r[clampi(X - 1, W) - o] * g1;
+                    acc += r[X - o] * g2;
+                    acc += r[clampi(X + 1, W) - o] * g3; acc += r[clampi(X + 2, W) - o] * g4;
                 }
-                T px = psi * ix, py = psi * iy;
-                sxy[k] += px * iy;
-                sx2[k] += px * ix;
-                sy2[k] += py * iy;
-                stx[k] += px * it;
-                sty[k] += py * it;
+                hs[ry * HW + hx] = acc;
+            }
+        }
+        __syncthreads();
+        // 3. vertical smoothing down a column segment (sliding window), blend with the smoothed Im1,
+        //    temporal difference at the centre.  Columns 64..67 are done by the first 16 threads.
+        auto vsmooth = [&](int bx, int sg) {
+            const int X = cx_(x0 - 2 + bx);
+            const int by0 = sg * BSEG;
+            if (by0 >= BH) return;
+            if (INTERIOR) {
+                const T* hcol = hs + bx;
+                T w0 = hcol[(by0 + 0) * HW], w1 = hcol[(by0 + 1) * HW], w2 = hcol[(by0 + 2) * HW], w3 = hcol[(by0 + 3) * HW];
+#pragma unroll
+                for (int j = 0; j < BSEG; j++) {
+                    const int by = by0 + j;
+                    if (by >= BH) break;
+                    T w4 = hcol[(by + 4) * HW];
+                    T acc = 0;
+                    acc += w0 * g0; acc += w1 * g1; acc += w2 * g2; acc += w3 * g3; acc += w4 * g4;
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+                    T s1v = s1c[(size_t)(y0 - 2 + by) * a.s1.pitch + X];
+                    T t = s1v * (T)0.4;
+                    bl[by * BW + bx] = t + acc * (T)0.6;
+                    int ccx = bx - 2, ccy = by - 2;
+                    if (ccx >= 0 && ccx < TX && ccy >= 0 && ccy < TY) sm_dt[ccy * TX + ccx] = acc - s1v;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < BSEG; j++) {
+                    const int by = by0 + j;
+                    if (by >= BH) break;
+                    const int Y = clampi(y0 - 2 + by, H), o = y0 - 4;
+                    T acc = 0;
+                    acc += hs[(clampi(Y - 2, H) - o) * HW + bx] * g0;
+                    acc += hs[(clampi(Y - 1, H) - o) * HW + bx] * g1;
+                    acc += hs[(Y - o) * HW + bx] * g2;
+                    acc += hs[(clampi(Y + 1, H) - o) * HW + bx] * g3;
+                    acc += hs[(clampi(Y + 2, H) - o) * HW + bx] * g4;
+                    T s1v = s1c[(size_t)Y * a.s1.pitch + X];
+                    T t = s1v * (T)0.4;
+                    bl[by * BW + bx] = t + acc * (T)0.6;
+                    int ccx = bx - 2, ccy = by - 2;
+                    if (ccx >= 0 && ccx < TX && ccy >= 0 && ccy < TY) sm_dt[ccy * TX + ccx] = acc - s1v;
+                }
+            }
+        };
+        vsmooth(col, seg);
+        if (tid < 4 * SEG) vsmooth(TX + (tid & 3), tid >> 2);
+        __syncthreads();
+        // 4. derivatives of the blend at the centre pixels (vertical window slides), psi products
+        if (col_ok) {
+            const int cy0 = seg * PPT;
+            if (INTERIOR) {
+                const T* bcol = bl + (col + 2);
+                T v0 = bcol[(cy0 + 0) * BW], v1 = bcol[(cy0 + 1) * BW], v2 = bcol[(cy0 + 2) * BW], v3 = bcol[(cy0 + 3) * BW];
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    const int cy = cy0 + k;
+                    T v4 = bcol[(cy + 4) * BW];
+                    const T* brow = bl + (cy + 2) * BW + col;
+                    T ix = 0, iy = 0;
+                    ix += brow[0] * d0; ix += brow[1] * d1; ix += brow[3] * d3; ix += brow[4] * d4;
+                    iy += v0 * d0; iy += v1 * d1; iy += v3 * d3; iy += v4 * d4;
+                    v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+                    T it = sm_dt[cy * TX + col];
+                    T psi = 0;
+                    if (active) {
+                        T t = it + ix * cdu[k] + iy * cdv[k];
+                        psi = psi_of(t * t, a.eps);
+                    }
+                    T px = psi * ix, py = psi * iy;
+                    sxy[k] += px * iy; sx2[k] += px * ix; sy2[k] += py * iy; stx[k] += px * it; sty[k] += py * it;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    const int cy = cy0 + k, Y = y0 + cy;
+                    if (Y >= H) continue;
+                    const int ox = x0 - 2, oy = y0 - 2;
+                    const T* brow = bl + (cy + 2) * BW;
+                    T ix = 0, iy = 0;
+                    ix += brow[clampi(PX - 2, W) - ox] * d0; ix += brow[clampi(PX - 1, W) - ox] * d1;
+                    ix += brow[clampi(PX + 1, W) - ox] * d3; ix += brow[clampi(PX + 2, W) - ox] * d4;
+                    iy += bl[(clampi(Y - 2, H) - oy) * BW + col + 2] * d0; iy += bl[(clampi(Y - 1, H) - oy) * BW + col + 2] * d1;
+                    iy += bl[(clampi(Y + 1, H) - oy) * BW + col + 2] * d3; iy += bl[(clampi(Y + 2, H) - oy) * BW + col + 2] * d4;
+                    T it = sm_dt[cy * TX + col];
+                    T psi = 0;
+                    if (active) {
+                        T t = it + ix * cdu[k] + iy * cdv[k];
+                        psi = psi_of(t * t, a.eps);
+                    }
+                    T px = psi * ix, py = psi * iy;
+                    sxy[k] += px * iy; sx2[k] += px * ix; sy2[k] += py * iy; stx[k] += px * it; sty[k] += py * it;
+                }
             }
         }
         __syncthreads();
@@ -547,70 +623,72 @@ __global__ void __launch_bounds__(256) k_fused_assemble(FusedArgs<T> a) {
     T* tu = sm_raw;
     T* tv = tu + UW * UH;
     T* tphi = sm_bl;
-    for (int i = tid; i < UW * UH; i += NT) {
-        int uy = i / UW, ux = i - uy * UW;
-        int Y = clampi(y0 - 1 + uy, H), X = clampi(x0 - 1 + ux, W);
-        size_t o = (size_t)Y * a.pitch + X;
-        T uv = a.u[o], vv = a.v[o];
-        tu[i] = a.du ? uv + a.du[o] : uv;
-        tv[i] = a.dv ? vv + a.dv[o] : vv;
-    }
-    __syncthreads();
-    for (int i = tid; i < PW * PH; i += NT) {
-        int py = i / PW, px = i - py * PW;
-        int X = x0 - 1 + px, Y = y0 - 1 + py;          // image coordinate of this phi entry
-        T val = 0;
-        if (X >= 0 && X < W && Y >= 0 && Y < H) {
-            int ui = py * UW + px;                      // same coordinate in the u tiles
-            T u0 = tu[ui], v0 = tv[ui];
-            T ux = 0, uy = 0, vx = 0, vy = 0;
-            if (X < W - 1) { ux = tu[ui + 1] - u0; vx = tv[ui + 1] - v0; }
-            if (Y < H - 1) { uy = tu[ui + UW] - u0; vy = tv[ui + UW] - v0; }
-            T t = ux * ux + uy * uy + vx * vx + vy * vy;
-            val = (T)0.5 / sqrt(t + a.eps);
+    auto load_uv = [&](bool with_increment) {
+        for (int uy = warp; uy < UH; uy += NWARP) {
+            const size_t ro = (size_t)cy_(y0 - 1 + uy) * a.pitch;
+            for (int ux = lane; ux < UW; ux += 32) {
+                size_t o = ro + cx_(x0 - 1 + ux);
+                T uv = a.u[o], vv = a.v[o];
+                if (with_increment) { uv += a.du[o]; vv += a.dv[o]; }
+                tu[uy * UW + ux] = uv;
+                tv[uy * UW + ux] = vv;
+            }
         }
-        tphi[i] = val;
+    };
+    load_uv(a.du != nullptr);
+    __syncthreads();
+    for (int py = warp; py < PH; py += NWARP) {
+        const int Y = y0 - 1 + py;
+        for (int px = lane; px < PW; px += 32) {
+            const int X = x0 - 1 + px;
+            T val = 0;
+            if (INTERIOR || (X >= 0 && X < W && Y >= 0 && Y < H)) {
+                int ui = py * UW + px;
+                T u0 = tu[ui], v0 = tv[ui];
+                T ux = 0, uy = 0, vx = 0, vy = 0;
+                if (INTERIOR || X < W - 1) { ux = tu[ui + 1] - u0; vx = tv[ui + 1] - v0; }
+                if (INTERIOR || Y < H - 1) { uy = tu[ui + UW] - u0; vy = tv[ui + UW] - v0; }
+                T t = ux * ux + uy * uy + vx * vx + vy * vy;
+                val = (T)0.5 / sqrt(t + a.eps);
+            }
+            tphi[py * PW + px] = val;
+        }
     }
     __syncthreads();
     if (a.du) {
-        for (int i = tid; i < UW * UH; i += NT) {
-            int uy = i / UW, ux = i - uy * UW;
-            int Y = clampi(y0 - 1 + uy, H), X = clampi(x0 - 1 + ux, W);
-            size_t o = (size_t)Y * a.pitch + X;
-            tu[i] = a.u[o];
-            tv[i] = a.v[o];
-        }
+        load_uv(false);
         __syncthreads();
     }
     // 6. Laplacian (fork quirk F3), right-hand sides, inverse diagonals
+    if (!col_ok) return;
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        int p = tid + k * NT, cx = p % TX, cy = p / TX;
-        int X = x0 + cx, Y = y0 + cy;
-        if (X >= W || Y >= H) continue;
-        const int pi = (cy + 1) * PW + (cx + 1), ui = (cy + 1) * UW + (cx + 1);
+        const int cy = seg * PPT + k, Y = y0 + cy, X = PX;
+        if (!INTERIOR && Y >= H) continue;
+        const int pi = (cy + 1) * PW + (col + 1), ui = (cy + 1) * UW + (col + 1);
         const T ph = tphi[pi];
+        const bool xr = INTERIOR || X < W - 1, xl = INTERIOR || X > 0, yd = INTERIOR || Y < H - 1, yu = INTERIOR || Y > 0;
         T lu = 0, lv = 0, cf = 0;
-        if (X < W - 1) {
+        if (xr) {
             lu -= (tu[ui + 1] - tu[ui]) * ph;
             lv -= (tv[ui + 1] - tv[ui]) * ph;
-            if (X > 0) {
+            if (xl) {
                 lu += (tu[ui] - tu[ui - 1]) * tphi[pi - 1];
                 lv += (tv[ui] - tv[ui - 1]) * tphi[pi - 1];
             }
         }
-        if (Y < H - 1) {
+        if (yd) {
             lu -= (tu[ui + UW] - tu[ui]) * ph;
             lv -= (tv[ui + UW] - tv[ui]) * ph;
-            if (Y > 0) {
+            if (yu) {
                 lu += (tu[ui] - tu[ui - UW]) * tphi[pi - PW];
                 lv += (tv[ui] - tv[ui - UW]) * tphi[pi - PW];
             }
         }
-        if (X > 0) cf += tphi[pi - 1];
-        if (X < W - 1) cf += ph;
-        if (Y > 0) cf += tphi[pi - PW];
-        if (Y < H - 1) cf += ph;
+        if (xl) cf += tphi[pi - 1];
+        if (xr) cf += ph;
+        if (yu) cf += tphi[pi - PW];
+        if (yd) cf += ph;
         cf *= a.alpha;
         T a_xy = sxy[k], a_x2 = sx2[k], a_y2 = sy2[k], a_tx = stx[k], a_ty = sty[k];
         if (C > 1) {
@@ -626,6 +704,19 @@ __global__ void __launch_bounds__(256) k_fused_assemble(FusedArgs<T> a) {
         a.bu[o] = -a_tx - a.alpha * lu;
         a.bv[o] = -a_ty - a.alpha * lv;
     }
+}
+
+template <typename T, int TX, int TY, int SEG>
+__global__ void __launch_bounds__(TX * SEG) k_fused_assemble(FusedArgs<T> a) {
+    __shared__ T sm_raw[(TY + 8) * (TX + 8) + (TY + 8) * (TX + 4)];
+    __shared__ T sm_bl[(TY + 4) * (TX + 4)];
+    __shared__ T sm_dt[TY * TX];
+    static_assert(2 * (TX + 2) * (TY + 2) <= (TY + 8) * (TX + 8) + (TY + 8) * (TX + 4), "u/v tiles alias raw + hs");
+    static_assert((TX + 1) * (TY + 1) <= (TY + 4) * (TX + 4), "phi tile aliases the blend tile");
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const bool interior = x0 >= 4 && y0 >= 4 && x0 + TX + 4 <= a.w && y0 + TY + 4 <= a.h;
+    if (interior) fused_assemble_body<T, TX, TY, SEG, true>(a, sm_raw, sm_bl, sm_dt);
+    else          fused_assemble_body<T, TX, TY, SEG, false>(a, sm_raw, sm_bl, sm_dt);
 }
 
 }  // namespace pf

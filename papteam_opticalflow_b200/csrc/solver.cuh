@@ -106,8 +106,8 @@ struct SorRunner {
     static constexpr int kR = kF64 ? 2 : 4;
     static constexpr int kNW = 16;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, simple_rb = false;
-    int forced_fuse = 0, coop_max_blocks = 1;
+    bool lex = false, simple_rb = false, use_tma = true;
+    int forced_fuse = 0, coop_max_blocks = 1, sms = 148;
     cudaStream_t st = nullptr;
 
     void init(int mode, int device, cudaStream_t stream) {
@@ -117,9 +117,15 @@ struct SorRunner {
         forced_fuse = e ? atoi(e) : 0;
         e = getenv("PF_SOR_SIMPLE");
         simple_rb = e && atoi(e);
+        e = getenv("PF_SOR_TMA");
+        use_tma = !(e && !atoi(e));
+        PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        if (!lex && !simple_rb && use_tma) {
+            size_t bytes = sizeof(SorStage<T, kR, kNW>) + 128;
+            PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        }
         if (lex) {
-            int sms = 0, coop = 0, per_sm = 0;
-            PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            int coop = 0, per_sm = 0;
             PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
             if (!coop) throw Error(PF_EUNSUPPORTED, "device lacks cooperative launch");
             PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_wavefront<T>, 256, 0));
@@ -161,6 +167,22 @@ struct SorRunner {
             SorTiling tx = sor_tiling(w, kSorRegionW, 2 * nsw), ty = sor_tiling(h, kRegionH, 2 * nsw);
             if (tx.ntiles == 0 || ty.ntiles == 0) throw Error(PF_EINVAL, "SOR tiling failed");
             a.du_in = done ? du : nullptr; a.dv_in = done ? dv : nullptr; a.du = du2; a.dv = dv2;
+            if (use_tma) {
+                // persistent, TMA-staged variant: one CTA per SM walks the tiles round-robin
+                SorMaps m;
+                m.phi = make_plane_map(a.phi, w, h, a.pitch, 72, kRegionH + 1);
+                m.dxy = make_plane_map(a.dxy, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.iu = make_plane_map(a.iu, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.iv = make_plane_map(a.iv, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.bu = make_plane_map(a.bu, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.bv = make_plane_map(a.bv, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.du = make_plane_map(done ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
+                m.dv = make_plane_map(done ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
+                int ntiles = tx.ntiles * ty.ntiles;
+                size_t smem = sizeof(SorStage<T, kR, kNW>) + 128;
+                k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+                    m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, nsw, done ? 1 : 0, tx.ntiles, ty.ntiles, tx.step, ty.step);
+            } else
             k_sor_rb_tile<T, kR, kNW><<<dim3(tx.ntiles, ty.ntiles), kNW * 32, 0, st>>>(a, nsw, tx.step, ty.step);
             launches++;
             std::swap(du, du2);
@@ -545,7 +567,7 @@ class Plan : public PlanBase {
                         fa.w = w; fa.h = h; fa.pitch = pitch;
                         fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = eps;
                         fa.g5 = g5; fa.d5 = d5;
-                        k_fused_assemble<T, kFTX, kFTY><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), 256, 0, st_>>>(fa);
+                        k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
                         launches_++;
                     } else {
                         // -- Phase2: flow derivatives + phi --
@@ -607,7 +629,7 @@ class Plan : public PlanBase {
     Params P;
 
   private:
-    static constexpr int kFTX = 64, kFTY = 16;   // output tile of k_fused_assemble
+    static constexpr int kFTX = 64, kFTY = kF64 ? 16 : 32, kFSEG = 8;   // k_fused_assemble tile (shared-memory bound), 512 threads
     bool lex_ = false, use_graph_ = true, fused_ = true, profiling_ = false, open_ = false;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;

@@ -15,6 +15,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace pf {
 namespace cg = cooperative_groups;
@@ -271,6 +272,198 @@ __global__ void __launch_bounds__(NW * 32, 1) k_sor_rb_tile(SorArgs<T> a, int ns
         } else if (v1) {
             a.du[o + 1] = du[r][1];
             a.dv[o + 1] = dv[r][1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast mode, production variant: the same register-resident red-black update as k_sor_rb_tile, run
+// as a PERSISTENT kernel (one CTA per SM, tiles dealt round-robin) whose next tile is staged by TMA
+// while the current one is being swept.
+//
+// Per tile one elected thread issues eight 2-D bulk tensor copies (cp.async.bulk.tensor -> SASS
+// UTMALDG) into a shared-memory stage -- phi as a 72 x (RH+1) box at (rx0-4, ry0-1) so that the
+// weights of the left / upper neighbours outside the region come along, the other seven planes as
+// 64 x RH boxes -- and arms one mbarrier with the byte count.  TMA zero-fills everything outside the
+// plane (negative coordinates, row padding, rows past the image), which is exactly the "phantom
+// pixel" convention of the update.  Threads wait on the mbarrier, pull their 2 x R patch from shared
+// memory into registers with conflict-free 8-byte loads, release the stage with one __syncthreads,
+// the next tile's copies are issued immediately and overlap the 2*nsw half-sweeps and the
+// write-back.  HBM/L2 reads, register compute and stores of different tiles therefore overlap on
+// every SM instead of alternating in lock-step across the chip.
+// ------------------------------------------------------------------------------------------------
+struct SorMaps {
+    CUtensorMap phi, dxy, iu, iv, bu, bv, du, dv;   // du/dv: the INPUT buffers of this pass
+};
+
+template <typename T, int R, int NW>
+struct SorStage {
+    static constexpr int RH = NW * R;
+    static constexpr int PHW = 72, PHH = RH + 1;   // phi box starts at rx0-4: TMA needs 16-byte aligned inner coordinates
+    alignas(128) T phi[PHH][PHW];
+    alignas(128) T pl[7][RH][kSorRegionW];   // dxy, iu, iv, bu, bv, du, dv (each plane a multiple of 128 B)
+};
+
+template <typename T, int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
+             T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y) {
+    static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
+    typedef typename Vec2<T>::type V2;
+    typedef SorStage<T, R, NW> Stage;
+    constexpr int RH = NW * R;
+    extern __shared__ unsigned char smem_raw[];
+    // TMA destinations must be 128-byte aligned; the dynamic segment is over-allocated by 128 bytes
+    Stage& st = *reinterpret_cast<Stage*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ T ex[2][NW][2][kSorRegionW];  // [du|dv][warp][top|bottom][x]
+    __shared__ __align__(8) uint64_t full_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int HL = 2 * nsw;
+    const int ntiles = ntx * nty;
+    const uint32_t stage_bytes = (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW + (has_input ? 7 : 5) * RH * kSorRegionW));
+    const T one_m = (T)1 - omega;
+
+    auto issue = [&](int tile) {
+        const int tx = tile % ntx, ty = tile / ntx;
+        const int rx0 = tx * step_x, ry0 = ty * step_y;
+        mbar_expect_tx(&full_bar, stage_bytes);
+        tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
+        tma_load_2d(&st.pl[0][0][0], &maps.dxy, rx0, ry0, &full_bar);
+        tma_load_2d(&st.pl[1][0][0], &maps.iu, rx0, ry0, &full_bar);
+        tma_load_2d(&st.pl[2][0][0], &maps.iv, rx0, ry0, &full_bar);
+        tma_load_2d(&st.pl[3][0][0], &maps.bu, rx0, ry0, &full_bar);
+        tma_load_2d(&st.pl[4][0][0], &maps.bv, rx0, ry0, &full_bar);
+        if (has_input) {
+            tma_load_2d(&st.pl[5][0][0], &maps.du, rx0, ry0, &full_bar);
+            tma_load_2d(&st.pl[6][0][0], &maps.dv, rx0, ry0, &full_bar);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) issue(tile);
+    uint32_t parity = 0;
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % ntx, ty = tile / ntx;
+        const int rx0 = tx * step_x, ry0 = ty * step_y;   // even by construction
+        const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
+
+        mbar_wait(&full_bar, parity);
+        parity ^= 1;
+
+        T w[R][2], dxy[R][2], iu[R][2], iv[R][2], bu[R][2], bv[R][2], du[R][2], dv[R][2];
+        T wl[R], wu[2];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int row = wp * R + r;
+            V2 t = *reinterpret_cast<const V2*>(&st.phi[row + 1][2 * lane + 4]);
+            w[r][0] = t.x * alpha; w[r][1] = t.y * alpha;
+            wl[r] = st.phi[row + 1][2 * lane + 3] * alpha;
+            t = *reinterpret_cast<const V2*>(&st.pl[0][row][2 * lane]); dxy[r][0] = t.x; dxy[r][1] = t.y;
+            t = *reinterpret_cast<const V2*>(&st.pl[1][row][2 * lane]); iu[r][0] = t.x; iu[r][1] = t.y;
+            t = *reinterpret_cast<const V2*>(&st.pl[2][row][2 * lane]); iv[r][0] = t.x; iv[r][1] = t.y;
+            t = *reinterpret_cast<const V2*>(&st.pl[3][row][2 * lane]); bu[r][0] = t.x; bu[r][1] = t.y;
+            t = *reinterpret_cast<const V2*>(&st.pl[4][row][2 * lane]); bv[r][0] = t.x; bv[r][1] = t.y;
+            if (has_input) {
+                t = *reinterpret_cast<const V2*>(&st.pl[5][row][2 * lane]); du[r][0] = t.x; du[r][1] = t.y;
+                t = *reinterpret_cast<const V2*>(&st.pl[6][row][2 * lane]); dv[r][0] = t.x; dv[r][1] = t.y;
+            } else {
+                du[r][0] = du[r][1] = dv[r][0] = dv[r][1] = 0;
+            }
+        }
+        {
+            V2 t = *reinterpret_cast<const V2*>(&st.phi[wp * R][2 * lane + 4]);
+            wu[0] = t.x * alpha; wu[1] = t.y * alpha;
+        }
+        auto publish = [&]() {
+            *reinterpret_cast<V2*>(&ex[0][wp][0][2 * lane]) = V2{du[0][0], du[0][1]};
+            *reinterpret_cast<V2*>(&ex[1][wp][0][2 * lane]) = V2{dv[0][0], dv[0][1]};
+            *reinterpret_cast<V2*>(&ex[0][wp][1][2 * lane]) = V2{du[R - 1][0], du[R - 1][1]};
+            *reinterpret_cast<V2*>(&ex[1][wp][1][2 * lane]) = V2{dv[R - 1][0], dv[R - 1][1]};
+        };
+        publish();
+        __syncthreads();   // stage consumed by everyone, exchange rows published
+        {
+            const int next = tile + gridDim.x;
+            if (tid == 0 && next < ntiles) issue(next);   // overlaps the sweeps below
+        }
+
+        for (int s = 0; s < nsw; s++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int p_top = c & 1, p_bot = (R - 1 + c) & 1;
+                T up_du = 0, up_dv = 0, dn_du = 0, dn_dv = 0;
+                if (wp > 0) {
+                    up_du = ex[0][wp - 1][1][2 * lane + p_top];
+                    up_dv = ex[1][wp - 1][1][2 * lane + p_top];
+                }
+                if (wp < NW - 1) {
+                    dn_du = ex[0][wp + 1][0][2 * lane + p_bot];
+                    dn_dv = ex[1][wp + 1][0][2 * lane + p_bot];
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int p = (r + c) & 1;
+                    T lw, ldu, ldv, rdu, rdv;
+                    if (p == 1) {
+                        lw = w[r][0]; ldu = du[r][0]; ldv = dv[r][0];
+                        rdu = __shfl_down_sync(0xffffffffu, du[r][0], 1);
+                        rdv = __shfl_down_sync(0xffffffffu, dv[r][0], 1);
+                        if (lane == 31) { rdu = 0; rdv = 0; }
+                    } else {
+                        lw = wl[r];
+                        ldu = __shfl_up_sync(0xffffffffu, du[r][1], 1);
+                        ldv = __shfl_up_sync(0xffffffffu, dv[r][1], 1);
+                        if (lane == 0) { ldu = 0; ldv = 0; }
+                        rdu = du[r][1]; rdv = dv[r][1];
+                    }
+                    T uw, udu, udv, ddu, ddv;
+                    if (r > 0) { uw = w[r - 1][p]; udu = du[r - 1][p]; udv = dv[r - 1][p]; }
+                    else       { uw = wu[p];       udu = up_du;        udv = up_dv; }
+                    if (r < R - 1) { ddu = du[r + 1][p]; ddv = dv[r + 1][p]; }
+                    else           { ddu = dn_du;        ddv = dn_dv; }
+                    const T cw = w[r][p];
+                    T s1 = bu[r][p] + lw * ldu + cw * rdu + uw * udu + cw * ddu;
+                    T s2 = bv[r][p] + lw * ldv + cw * rdv + uw * udv + cw * ddv;
+                    s1 -= dxy[r][p] * dv[r][p];
+                    T nu = one_m * du[r][p] + iu[r][p] * s1;
+                    s2 -= dxy[r][p] * nu;
+                    T nv = one_m * dv[r][p] + iv[r][p] * s2;
+                    du[r][p] = nu;
+                    dv[r][p] = nv;
+                }
+                __syncthreads();
+                publish();
+                __syncthreads();
+            }
+        }
+
+        const int ox_lo = tx > 0 ? rx0 + HL : 0;
+        const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
+        const int oy_lo = ty > 0 ? ry0 + HL : 0;
+        const int oy_hi = (ry0 + RH >= H) ? H : ry0 + RH - HL;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int y = ya + r;
+            if (y < oy_lo || y >= oy_hi) continue;
+            bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
+            size_t o = (size_t)y * P + xa;
+            if (v0 && v1) {
+                *reinterpret_cast<V2*>(du_out + o) = V2{du[r][0], du[r][1]};
+                *reinterpret_cast<V2*>(dv_out + o) = V2{dv[r][0], dv[r][1]};
+            } else if (v0) {
+                du_out[o] = du[r][0];
+                dv_out[o] = dv[r][0];
+            } else if (v1) {
+                du_out[o + 1] = du[r][1];
+                dv_out[o + 1] = dv[r][1];
+            }
         }
     }
 }
