@@ -446,6 +446,13 @@ struct FusedArgs {
 // reciprocal square root (2 ulp), far below the single-precision noise of the products it scales.
 __device__ __forceinline__ double psi_of(double t, double eps) { return 1.0 / (2.0 * sqrt(t + eps)); }
 __device__ __forceinline__ float psi_of(float t, float eps) { return 0.5f * rsqrtf(t + eps); }
+// the same split for phi = 0.5/sqrt(t+eps), the channel mean and omega/denominator
+__device__ __forceinline__ double phi_of(double t, double eps) { return 0.5 / sqrt(t + eps); }
+__device__ __forceinline__ float phi_of(float t, float eps) { return 0.5f * rsqrtf(t + eps); }
+__device__ __forceinline__ double mean_of(double s, int c, double) { return s / (double)c; }
+__device__ __forceinline__ float mean_of(float s, int, float inv_c) { return s * inv_c; }
+__device__ __forceinline__ double ratio_of(double a, double b) { return a / b; }
+__device__ __forceinline__ float ratio_of(float a, float b) { return __fdividef(a, b); }
 
 // Thread layout (256 threads, 8 warps): tile rows are dealt to warps and columns to lanes when
 // staging (coalesced, conflict free, no div/mod); for the vertical filters, the derivative stage

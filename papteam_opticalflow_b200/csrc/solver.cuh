@@ -12,6 +12,7 @@
 #include "geometry.hpp"
 #include "kernels.cuh"
 #include "sor.cuh"
+#include "fused_tma.cuh"
 
 namespace pf {
 
@@ -212,6 +213,11 @@ class Plan : public PlanBase {
         use_graph_ = !(e && atoi(e)) && !lex_;
         e = getenv("PF_UNFUSED");
         fused_ = !(e && atoi(e));
+        e = getenv("PF_FUSED_TMA");
+        fused_tma_ = !(e && !atoi(e));
+        if (fused_tma_)
+            PF_CUDA(cudaFuncSetAttribute(k_fused_tma<T, kFTY, kFSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(FusedSmem<T, kFTY>) + 128)));
         PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
         allocate();
@@ -541,6 +547,11 @@ class Plan : public PlanBase {
             filter_h(f1, tmp, g5);
             filter_v(tmp, s1, g5);
 
+            FusedMaps fmaps;
+            if (fused_ && fused_tma_) {
+                fmaps.wf = make_image_map(wf.p, w, h, fc_, wf.pitch, wf.plane, 72, kFTY + 8);
+                fmaps.s1 = make_image_map(s1.p, w, h, fc_, s1.pitch, s1.plane, 72, kFTY + 4);
+            }
             const int n_outer = P.n_outer + k, n_sor = P.n_sor + 3 * k;
             for (int it = 0; it < n_outer; it++) {
                 if (!fused_) {
@@ -567,6 +578,10 @@ class Plan : public PlanBase {
                         fa.w = w; fa.h = h; fa.pitch = pitch;
                         fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = eps;
                         fa.g5 = g5; fa.d5 = d5;
+                        if (fused_tma_) {
+                            size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
+                            k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(fmaps, fa);
+                        } else
                         k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
                         launches_++;
                     } else {
@@ -630,7 +645,7 @@ class Plan : public PlanBase {
 
   private:
     static constexpr int kFTX = 64, kFTY = kF64 ? 16 : 32, kFSEG = 8;   // k_fused_assemble tile (shared-memory bound), 512 threads
-    bool lex_ = false, use_graph_ = true, fused_ = true, profiling_ = false, open_ = false;
+    bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;
     std::vector<Level> geo_;

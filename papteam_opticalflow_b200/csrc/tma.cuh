@@ -43,6 +43,22 @@ inline CUtensorMap make_plane_map(const T* base, int w, int h, int pitch, int bo
     return m;
 }
 
+// planar multi-channel image as a (w, h, c) tensor; boxes are box_w x box_h x 1 (one channel)
+template <typename T>
+inline CUtensorMap make_image_map(const T* base, int w, int h, int c, int pitch, size_t plane, int box_w, int box_h) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)c};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(T), (cuuint64_t)plane * sizeof(T)};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = tensor_map_encoder()(&m, dt, 3, const_cast<T*>(base), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(PF_ECUDA, "cuTensorMapEncodeTiled(3d) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 // ---- device: mbarrier + bulk tensor copy ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -76,6 +92,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
