@@ -85,6 +85,11 @@ int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const dou
                                const double* im2, int pyramidLevels, int nCores, int h, int w,
                                int c, int mode, int device, double* timings);
 
+/* The one-shot and batch entry points keep up to 16 idle plans (device arena + CUDA graph) in a
+ * pool keyed by every parameter, so repeated calls pay neither allocation nor graph capture;
+ * pf_pool_clear destroys the idle ones and returns how many it freed. */
+int pf_pool_clear(void);
+
 /* ---- plans: device arena + captured CUDA graph for one (h, w, c, parameters, mode, device) ---
  * levels > 0 selects the fork's explicit level count, otherwise minWidth decides. */
 int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,

@@ -44,6 +44,7 @@ def lib():
         "pf_level_geometry": (i, [i, i, d, i, ip, ip]),
         "pf_coarse2fine_flow": (i, [dp, dp, dp, dp, dp, d, d, i, i, i, i, i, i, i, i, i, i, dp]),
         "pf_coarse2fine_flow_levels": (i, [dp, dp, dp, dp, dp, i, i, i, i, i, i, i, dp]),
+        "pf_pool_clear": (i, []),
         "pf_plan_create": (i, [C.POINTER(v), i, i, i, d, d, i, i, i, i, i, i, i, i]),
         "pf_plan_destroy": (i, [v]),
         "pf_plan_levels": (i, [v]),

@@ -75,6 +75,73 @@ int stage_prologue(int h, int w, int c, int mode, int device) {
     return PF_OK;
 }
 
+
+// ---- plan pool: one-shot and batch entry points reuse arenas + captured graphs across calls ------
+struct PoolEntry {
+    Params key;
+    pf_plan* plan;
+    bool busy;
+    unsigned long long stamp;
+};
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+unsigned long long g_pool_clock = 0;
+const size_t kPoolMax = 16;
+
+bool same_params(const Params& a, const Params& b) {
+    return a.h == b.h && a.w == b.w && a.c == b.c && a.alpha == b.alpha && a.ratio == b.ratio &&
+           a.min_width == b.min_width && a.levels == b.levels && a.n_outer == b.n_outer && a.n_inner == b.n_inner &&
+           a.n_sor == b.n_sor && a.col_type == b.col_type && a.mode == b.mode && a.device == b.device;
+}
+
+void pool_release(pf_plan* pl) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    for (auto& e : g_pool)
+        if (e.plan == pl) {
+            e.busy = false;
+            e.stamp = ++g_pool_clock;
+            return;
+        }
+}
+
+}  // namespace
+
+extern "C" int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                              int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device);
+extern "C" int pf_plan_destroy(pf_plan* plan);
+
+namespace {
+
+// returns an idle pooled plan for these parameters, creating one if needed (rc != 0 on failure)
+pf_plan* pool_acquire(const Params& p, int& rc) {
+    rc = PF_OK;
+    std::vector<pf_plan*> evict;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        for (auto& e : g_pool)
+            if (!e.busy && same_params(e.key, p)) {
+                e.busy = true;
+                return e.plan;
+            }
+        while (g_pool.size() >= kPoolMax) {     // drop the least recently used idle plan
+            size_t best = g_pool.size();
+            for (size_t i = 0; i < g_pool.size(); i++)
+                if (!g_pool[i].busy && (best == g_pool.size() || g_pool[i].stamp < g_pool[best].stamp)) best = i;
+            if (best == g_pool.size()) break;
+            evict.push_back(g_pool[best].plan);
+            g_pool.erase(g_pool.begin() + (long)best);
+        }
+    }
+    for (pf_plan* e : evict) pf_plan_destroy(e);
+    pf_plan* pl = nullptr;
+    rc = pf_plan_create(&pl, p.h, p.w, p.c, p.alpha, p.ratio, p.min_width, p.levels, p.n_outer, p.n_inner, p.n_sor,
+                        p.col_type, p.mode, p.device);
+    if (rc) return nullptr;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    g_pool.push_back(PoolEntry{p, pl, true, ++g_pool_clock});
+    return pl;
+}
+
 }  // namespace
 
 extern "C" {
@@ -240,13 +307,12 @@ int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im
                         const double* im2, double alpha, double ratio, int minWidth, int nOuter,
                         int nInner, int nSOR, int colType, int h, int w, int c, int mode, int device,
                         double* timings) {
-    pf_plan* pl = nullptr;
-    int r = pf_plan_create(&pl, h, w, c, alpha, ratio, minWidth, 0, nOuter, nInner, nSOR, colType, mode, device);
+    int r = PF_OK;
+    Params p{h, w, c, alpha, ratio, minWidth, 0, nOuter, nInner, nSOR, colType, mode, device};
+    pf_plan* pl = pool_acquire(p, r);
     if (r) return r;
     r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
-    std::string keep = g_err;
-    pf_plan_destroy(pl);
-    if (r) g_err = keep;
+    pool_release(pl);
     return r;
 }
 
@@ -255,15 +321,30 @@ int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const dou
                                int mode, int device, double* timings) {
     (void)nCores;
     if (pyramidLevels < 1) return fail(PF_EINVAL, "pyramidLevels must be >= 1");
-    pf_plan* pl = nullptr;
     // hard-coded solver constants of the fork: S/OpticalFlow.cpp:747-751; colType 0: wrapper :22
-    int r = pf_plan_create(&pl, h, w, c, 0.012, 0.75, 20, pyramidLevels, 7, 1, 30, 0, mode, device);
+    int r = PF_OK;
+    Params p{h, w, c, 0.012, 0.75, 20, pyramidLevels, 7, 1, 30, 0, mode, device};
+    pf_plan* pl = pool_acquire(p, r);
     if (r) return r;
     r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
-    std::string keep = g_err;
-    pf_plan_destroy(pl);
-    if (r) g_err = keep;
+    pool_release(pl);
     return r;
+}
+
+int pf_pool_clear(void) {
+    std::vector<pf_plan*> all;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size();)
+            if (!g_pool[i].busy) {
+                all.push_back(g_pool[i].plan);
+                g_pool.erase(g_pool.begin() + (long)i);
+            } else {
+                i++;
+            }
+    }
+    for (pf_plan* p : all) pf_plan_destroy(p);
+    return (int)all.size();
 }
 
 int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* const* warpI2,
@@ -293,8 +374,9 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     for (int wk = 0; wk < nworkers; wk++) {
         workers.emplace_back([&, wk]() {
             const int d = wk % ndevices;
-            pf_plan* pl = nullptr;
-            int r = pf_plan_create(&pl, h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[d]);
+            int r = PF_OK;
+            Params pp{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[d]};
+            pf_plan* pl = pool_acquire(pp, r);
             // pair p belongs to device p % ndevices; workers of one device share its queue
             while (r == PF_OK) {
                 int k = next[(size_t)d].fetch_add(1);
@@ -303,7 +385,7 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                 r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], nullptr);
             }
             if (r) messages[(size_t)wk] = g_err;
-            if (pl) pf_plan_destroy(pl);
+            if (pl) pool_release(pl);
             status[(size_t)wk] = r;
         });
     }

@@ -214,7 +214,7 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
 
 def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,
                            nInnerFPIterations=1, nSORIterations=30, colType=0, levels=0, mode=None,
-                           devices=None):
+                           devices=None, outs=None):
     """Solve a list of independent (im1, im2) pairs, pair p on devices[p % len(devices)], no
     collective.  Returns ([(u, v, im2W), ...], wall_seconds)."""
     L = _lib.lib()
@@ -229,7 +229,8 @@ def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFP
         if a.shape != pairs[0][0].shape or b.shape != a.shape:
             raise ValueError("all images of a batch must share one shape")
     h, w, c = pairs[0][0].shape
-    outs = [(np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))) for _ in range(n)]
+    if outs is None:
+        outs = [(np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))) for _ in range(n)]
     arr = lambda xs: (dp * n)(*[_ptr(x) for x in xs])  # noqa: E731
     dev = (C.c_int * len(devices))(*devices)
     secs = C.c_double()
