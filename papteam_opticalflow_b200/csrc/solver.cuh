@@ -104,12 +104,19 @@ template <typename T>
 struct SorRunner {
     static constexpr bool kF64 = sizeof(T) == 8;
     // tile-kernel shape: FP32 64x64 regions (R=4, 16 warps), FP64 64x32 (R=2)
-    static constexpr int kR = kF64 ? 2 : 4;
-    static constexpr int kNW = 16;
+#ifndef PF_SOR_R
+#define PF_SOR_R 8
+#define PF_SOR_NW 8
+#endif
+    static constexpr int kR = kF64 ? 2 : PF_SOR_R;
+    static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, simple_rb = false, use_tma = true;
+    bool lex = false, simple_rb = false, use_tma = true, packed = false;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148;
     cudaStream_t st = nullptr;
+
+    // stage + double-buffered exchange rows + alignment slack
+    static size_t sor_smem_bytes() { return sizeof(SorStage<T, kR, kNW>) + sizeof(T) * 2 * 2 * kNW * 2 * kSorRegionW + 128; }
 
     void init(int mode, int device, cudaStream_t stream) {
         lex = mode_is_lex(mode);
@@ -121,9 +128,13 @@ struct SorRunner {
         e = getenv("PF_SOR_TMA");
         use_tma = !(e && !atoi(e));
         PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        e = getenv("PF_SOR_PACKED");
+        packed = !kF64 && !(e && !atoi(e));
         if (!lex && !simple_rb && use_tma) {
-            size_t bytes = sizeof(SorStage<T, kR, kNW>) + 128;
+            size_t bytes = sor_smem_bytes();
             PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            if constexpr (!kF64 && kR == 4)
+                PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma_pk<kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         }
         if (lex) {
             int coop = 0, per_sm = 0;
@@ -180,7 +191,16 @@ struct SorRunner {
                 m.du = make_plane_map(done ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
                 m.dv = make_plane_map(done ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
                 int ntiles = tx.ntiles * ty.ntiles;
-                size_t smem = sizeof(SorStage<T, kR, kNW>) + 128;
+                size_t smem = sor_smem_bytes();
+                bool launched = false;
+                if constexpr (!kF64 && kR == 4) {
+                    if (packed) {
+                        k_sor_rb_tma_pk<kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+                            m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, nsw, done ? 1 : 0, tx.ntiles, ty.ntiles, tx.step, ty.step);
+                        launched = true;
+                    }
+                }
+                if (!launched)
                 k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
                     m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, nsw, done ? 1 : 0, tx.ntiles, ty.ntiles, tx.step, ty.step);
             } else
