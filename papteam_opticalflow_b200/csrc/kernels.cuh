@@ -70,6 +70,57 @@ __global__ void k_filter_v(Img<T> src, Img<T> dst, Taps<T> t) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Separable filter, both passes in one kernel (Image::imfilter_hv, S/Image.h:1347-1356): a 64 x 16
+// output tile per CTA, the raw tile (halo fh in x, fv in y) staged in shared memory with replicated
+// borders, the horizontal pass written to a second shared tile, the vertical pass to global.
+// Replicating raw rows commutes with the horizontal pass, and the horizontal pass is only evaluated
+// at in-image columns, so this is exactly vfiltering(hfiltering(src)) with the reference's clamping.
+// A half-width of 0 with tap 1.0 makes a pass the identity (used for the one-directional filters).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_filter_hv(Img<T> src, Img<T> dst, Taps<T> th, Taps<T> tv) {
+    constexpr int TX = 64, TY = 16, MAXH = kMaxHalf;
+    __shared__ T raw[(TY + 2 * MAXH) * (TX + 2 * MAXH)];
+    __shared__ T hs[(TY + 2 * MAXH) * TX];
+    __shared__ T tap_h[2 * MAXH + 1], tap_v[2 * MAXH + 1];   // dynamic tap index: keep them out of local memory
+    if (threadIdx.x < 2 * MAXH + 1) {
+        tap_h[threadIdx.x] = th.v[threadIdx.x];
+        tap_v[threadIdx.x] = tv.v[threadIdx.x];
+    }
+    const int fh = th.half, fv = tv.half;
+    const int RWd = TX + 2 * fh, RHt = TY + 2 * fv;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, k = blockIdx.z;
+    const int W = src.w, H = src.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T* sp = src.ch(k);
+    for (int ry = warp; ry < RHt; ry += 8) {
+        const T* row = sp + (size_t)clampi(y0 - fv + ry, H) * src.pitch;
+        for (int rx = lane; rx < RWd; rx += 32) raw[ry * RWd + rx] = row[clampi(x0 - fh + rx, W)];
+    }
+    __syncthreads();
+    for (int ry = warp; ry < RHt; ry += 8) {
+        const T* r = raw + ry * RWd;
+        for (int cx = lane; cx < TX; cx += 32) {
+            T acc = 0;
+            for (int l = 0; l <= 2 * fh; l++) acc += r[cx + l] * tap_h[l];
+            hs[ry * TX + cx] = acc;
+        }
+    }
+    __syncthreads();
+    const int cx = threadIdx.x & (TX - 1), seg = threadIdx.x / TX;     // 4 row segments of 4 rows
+    const int X = x0 + cx;
+    if (X >= W) return;
+#pragma unroll
+    for (int j = 0; j < TY / 4; j++) {
+        const int cy = seg * (TY / 4) + j, Y = y0 + cy;
+        if (Y >= H) break;
+        T acc = 0;
+        for (int l = 0; l <= 2 * fv; l++) acc += hs[(cy + l) * TX + cx] * tap_v[l];
+        dst.ch(k)[(size_t)Y * dst.pitch + X] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bilinear sampler (S/ImageProcessing.h:138-157).  Coordinates stay in double in BOTH modes
 // (x = j + u at j ~ 3840 has only 2.4e-4 px resolution in FP32): the integer
 // part comes from C truncation toward zero, the fraction is clamped to [0,1], taps are
@@ -152,6 +203,32 @@ __global__ void k_im2feature(Img<T> im, Img<T> feat, Taps<T> d5, int swap) {
 // Bilinear warp with Im1 fallback outside the image (S/ImageProcessing.h:483-503), optionally
 // preceded by the flow update u += du, v += dv of S/OpticalFlow.cpp:513-514 (du == nullptr: none).
 // ---------------------------------------------------------------------------------------------
+// Sampling position of pixel j displaced by flow value f, split into integer part and fraction
+// exactly as the reference's double arithmetic would (x = j + f; xx = (int)x; dx = x - xx for the
+// in-image case x >= 0, where truncation is floor).  The FP32 overload needs no FP64 instruction:
+// floor(j + f) = j + floor(f) and f - floor(f) is exact in single precision, so the tap indices, the
+// weights and the out-of-image decision are identical to evaluating j + (double)f.
+struct SamplePos {
+    int i;        // integer part
+    bool out;     // x < 0 || x > n-1
+};
+__device__ __forceinline__ SamplePos sample_pos(int j, double f, int n, double& frac) {
+    double x = (double)j + f;
+    SamplePos p;
+    p.out = x < 0 || x > n - 1;
+    p.i = (int)x;
+    frac = fmax(fmin(x - p.i, 1.0), 0.0);
+    return p;
+}
+__device__ __forceinline__ SamplePos sample_pos(int j, float f, int n, float& frac) {
+    float fl = floorf(f);
+    frac = f - fl;
+    SamplePos p;
+    p.i = j + (int)fl;
+    p.out = p.i < 0 || p.i > n - 1 || (p.i == n - 1 && frac > 0.f);
+    return p;
+}
+
 template <typename T>
 __global__ void k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
                               T* __restrict__ v, const T* __restrict__ du,
@@ -166,14 +243,28 @@ __global__ void k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict
         u[of] = uu;
         v[of] = vv;
     }
-    double sx = (double)x + (double)uu, sy = (double)y + (double)vv;
+    const int W = im1.w, H = im1.h;
+    T fx, fy;
+    SamplePos px = sample_pos(x, uu, W, fx), py = sample_pos(y, vv, H, fy);
     size_t o = (size_t)y * im1.pitch + x;
-    if (sx < 0 || sx > im1.w - 1 || sy < 0 || sy > im1.h - 1) {
+    if (px.out || py.out) {
         for (int k = 0; k < im1.c; k++) warp.ch(k)[o] = im1.ch(k)[o];
         return;
     }
-    Bilin<T> b(sx, sy, im1.w, im1.h);
-    for (int k = 0; k < im1.c; k++) warp.ch(k)[o] = b.sample(im2.ch(k), im2.pitch);
+    const int x0 = clampi(px.i, W), x1 = clampi(px.i + 1, W), y0 = clampi(py.i, H), y1 = clampi(py.i + 1, H);
+    const T ax0 = fabs((T)1 - fx), ax1 = fabs((T)0 - fx), ay0 = fabs((T)1 - fy), ay1 = fabs((T)0 - fy);
+    const T w00 = ax0 * ay0, w01 = ax0 * ay1, w10 = ax1 * ay0, w11 = ax1 * ay1;
+    const size_t o00 = (size_t)y0 * im2.pitch + x0, o01 = (size_t)y1 * im2.pitch + x0;
+    const size_t o10 = (size_t)y0 * im2.pitch + x1, o11 = (size_t)y1 * im2.pitch + x1;
+    for (int k = 0; k < im1.c; k++) {
+        const T* p = im2.ch(k);
+        T acc = 0;
+        acc += p[o00] * w00;
+        acc += p[o01] * w01;
+        acc += p[o10] * w10;
+        acc += p[o11] * w11;
+        warp.ch(k)[o] = acc;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -453,6 +453,12 @@ class Plan : public PlanBase {
         launches_++;
     }
 
+    // h then v pass in one kernel (no intermediate plane)
+    void filter_hv(const Img<T>& s, const Img<T>& d, const Taps<T>& th, const Taps<T>& tv) {
+        k_filter_hv<T><<<dim3(ceil_div(s.w, 64), ceil_div(s.h, 16), s.c), 256, 0, st_>>>(s, d, th, tv);
+        launches_++;
+    }
+
     void run_solve() {
         if (!use_graph_) {
             enqueue_solve();
@@ -510,10 +516,8 @@ class Plan : public PlanBase {
                 Img<T> blurred = src;
                 if (g.half > 0) {   // half-width 0 is the identity filter (level 1, quirk Q2)
                     Taps<T> gt = make_taps<T>(g.taps.data(), g.half);
-                    Img<T> tmp = view(b_tmp_, src.w, src.h, src.c);
                     blurred = view(b_out_, src.w, src.h, src.c);
-                    filter_h(src, tmp, gt);
-                    filter_v(tmp, blurred, gt);
+                    filter_hv(src, blurred, gt, gt);
                 }
                 k_resize<T><<<grid2(g.w, g.h), 128, 0, st_>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
                 launches_++;
@@ -564,8 +568,7 @@ class Plan : public PlanBase {
             // Im1 is constant within a level: its smoothed copy is computed once instead of every
             // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
             set_phase(PF_T_PHASE1_GENERATE, k);
-            filter_h(f1, tmp, g5);
-            filter_v(tmp, s1, g5);
+            filter_hv(f1, s1, g5, g5);
 
             FusedMaps fmaps;
             if (fused_ && fused_tma_) {
@@ -645,9 +648,11 @@ class Plan : public PlanBase {
             const Img<T>& im1 = pyr1_[0];
             const Img<T>& im2 = pyr2_[0];
             Img<T> ix = view(b_ix_, P.w, P.h, P.c), iy = view(b_iy_, P.w, P.h, P.c), ixy = view(b_ixy_, P.w, P.h, P.c);
-            filter_h(im2, ix, d3);
-            filter_v(im2, iy, d3);
-            filter_v(ix, ixy, d3);
+            const double one[1] = {1.0};
+            const Taps<T> id = make_taps<T>(one, 0);
+            filter_hv(im2, ix, d3, id);
+            filter_hv(im2, iy, id, d3);
+            filter_hv(im2, ixy, d3, d3);
             k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, d_warp_);
             Img<T> uo = view(u_, P.w, P.h, 1), vo = view(v_, P.w, P.h, 1);
             k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
