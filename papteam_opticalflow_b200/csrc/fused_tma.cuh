@@ -47,8 +47,11 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     static_assert(TY % SEG == 0, "tile height must split into SEG segments");
     static_assert(2 * UW * UH <= RHt * HW + SH * BW, "u/v tiles alias hs + bl");
 
-    extern __shared__ unsigned char smem_dyn[];
-    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+    // the alignment is declared on the dynamic segment itself (TMA destinations need 128 B); going
+    // through an integer round-up would make the compiler lose the shared address space and emit
+    // generic LD/ST instead of LDS/STS for every tile access
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_dyn);
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ T sm_phi[PW * PH];
 

@@ -669,7 +669,11 @@ class Plan : public PlanBase {
     Params P;
 
   private:
-    static constexpr int kFTX = 64, kFTY = kF64 ? 16 : 32, kFSEG = 8;   // k_fused_assemble tile (shared-memory bound), 512 threads
+#ifndef PF_FUSED_TY
+#define PF_FUSED_TY 16
+#define PF_FUSED_SEG 4
+#endif
+    static constexpr int kFTX = 64, kFTY = kF64 ? 16 : PF_FUSED_TY, kFSEG = kF64 ? 8 : PF_FUSED_SEG;   // k_fused_* tile, 64*SEG threads
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;

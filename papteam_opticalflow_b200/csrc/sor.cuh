@@ -312,13 +312,14 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
     typedef typename Vec2<T>::type V2;
     typedef SorStage<T, R, NW> Stage;
     constexpr int RH = NW * R;
-    extern __shared__ unsigned char smem_raw[];
-    // TMA destinations must be 128-byte aligned; the dynamic segment is over-allocated by 128 bytes
-    Stage& st = *reinterpret_cast<Stage*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // TMA destinations must be 128-byte aligned: declared on the dynamic segment (an integer round-up
+    // would demote every stage access from LDS to a generic LD)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     // exchange rows between warps, double buffered by half-sweep parity so that ONE barrier per
     // half-sweep suffices: [buffer][du|dv][warp][top|bottom][x]
     typedef T ExBuf[2][NW][2][kSorRegionW];
-    ExBuf* ex = reinterpret_cast<ExBuf*>(reinterpret_cast<unsigned char*>(&st) + sizeof(Stage));
+    ExBuf* ex = reinterpret_cast<ExBuf*>(smem_raw + sizeof(Stage));
     __shared__ __align__(8) uint64_t full_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -491,8 +492,8 @@ k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out
                 int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y) {
     constexpr int R = 4, RH = NW * R;
     typedef SorStage<float, R, NW> Stage;
-    extern __shared__ unsigned char smem_raw[];
-    Stage& st = *reinterpret_cast<Stage*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     __shared__ float ex[2][2][NW][2][2][32];   // [buffer][du|dv][warp][top|bottom][column parity][lane]
     __shared__ __align__(8) uint64_t full_bar;
 
