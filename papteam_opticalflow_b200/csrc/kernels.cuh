@@ -229,41 +229,81 @@ __device__ __forceinline__ SamplePos sample_pos(int j, float f, int n, float& fr
     return p;
 }
 
+// One thread handles kWarpPix pixels 32 columns apart: the flow loads of all of them are issued
+// first, then per channel all 4*kWarpPix gathers, so each thread keeps 16+ independent loads in
+// flight (the kernel is latency bound otherwise: two dependent memory round trips per pixel).
+constexpr int kWarpPix = 4;
+
 template <typename T>
-__global__ void k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
+__global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
                               T* __restrict__ v, const T* __restrict__ du,
                               const T* __restrict__ dv, int fpitch) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= im1.w) return;
-    size_t of = (size_t)y * fpitch + x;
-    T uu = u[of], vv = v[of];
-    if (du) {
-        uu += du[of];
-        vv += dv[of];
-        u[of] = uu;
-        v[of] = vv;
+    const int W = im1.w, H = im1.h, y = blockIdx.y;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int xb = (blockIdx.x * (blockDim.x >> 5) + wrp) * (32 * kWarpPix) + lane;   // first pixel of this thread
+    T uu[kWarpPix], vv[kWarpPix];
+#pragma unroll
+    for (int i = 0; i < kWarpPix; i++) {
+        const int x = xb + 32 * i;
+        uu[i] = 0; vv[i] = 0;
+        if (x < W) {
+            const size_t of = (size_t)y * fpitch + x;
+            uu[i] = u[of]; vv[i] = v[of];
+            if (du) { uu[i] += du[of]; vv[i] += dv[of]; }
+        }
     }
-    const int W = im1.w, H = im1.h;
-    T fx, fy;
-    SamplePos px = sample_pos(x, uu, W, fx), py = sample_pos(y, vv, H, fy);
-    size_t o = (size_t)y * im1.pitch + x;
-    if (px.out || py.out) {
-        for (int k = 0; k < im1.c; k++) warp.ch(k)[o] = im1.ch(k)[o];
-        return;
+    size_t o00[kWarpPix], o01[kWarpPix], o10[kWarpPix], o11[kWarpPix];
+    T w00[kWarpPix], w01[kWarpPix], w10[kWarpPix], w11[kWarpPix];
+    bool inside[kWarpPix];
+#pragma unroll
+    for (int i = 0; i < kWarpPix; i++) {
+        const int x = xb + 32 * i;
+        inside[i] = false;
+        o00[i] = o01[i] = o10[i] = o11[i] = 0;
+        w00[i] = w01[i] = w10[i] = w11[i] = 0;
+        if (x >= W) continue;
+        if (du) {
+            const size_t of = (size_t)y * fpitch + x;
+            u[of] = uu[i];
+            v[of] = vv[i];
+        }
+        T fx, fy;
+        const SamplePos px = sample_pos(x, uu[i], W, fx), py = sample_pos(y, vv[i], H, fy);
+        if (px.out || py.out) continue;
+        inside[i] = true;
+        const int x0 = clampi(px.i, W), x1 = clampi(px.i + 1, W), y0 = clampi(py.i, H), y1 = clampi(py.i + 1, H);
+        const T ax0 = fabs((T)1 - fx), ax1 = fabs((T)0 - fx), ay0 = fabs((T)1 - fy), ay1 = fabs((T)0 - fy);
+        w00[i] = ax0 * ay0; w01[i] = ax0 * ay1; w10[i] = ax1 * ay0; w11[i] = ax1 * ay1;
+        o00[i] = (size_t)y0 * im2.pitch + x0; o01[i] = (size_t)y1 * im2.pitch + x0;
+        o10[i] = (size_t)y0 * im2.pitch + x1; o11[i] = (size_t)y1 * im2.pitch + x1;
     }
-    const int x0 = clampi(px.i, W), x1 = clampi(px.i + 1, W), y0 = clampi(py.i, H), y1 = clampi(py.i + 1, H);
-    const T ax0 = fabs((T)1 - fx), ax1 = fabs((T)0 - fx), ay0 = fabs((T)1 - fy), ay1 = fabs((T)0 - fy);
-    const T w00 = ax0 * ay0, w01 = ax0 * ay1, w10 = ax1 * ay0, w11 = ax1 * ay1;
-    const size_t o00 = (size_t)y0 * im2.pitch + x0, o01 = (size_t)y1 * im2.pitch + x0;
-    const size_t o10 = (size_t)y0 * im2.pitch + x1, o11 = (size_t)y1 * im2.pitch + x1;
     for (int k = 0; k < im1.c; k++) {
         const T* p = im2.ch(k);
-        T acc = 0;
-        acc += p[o00] * w00;
-        acc += p[o01] * w01;
-        acc += p[o10] * w10;
-        acc += p[o11] * w11;
-        warp.ch(k)[o] = acc;
+        const T* q = im1.ch(k);
+        T a00[kWarpPix], a01[kWarpPix], a10[kWarpPix], a11[kWarpPix];
+#pragma unroll
+        for (int i = 0; i < kWarpPix; i++) {
+            const int x = xb + 32 * i;
+            if (inside[i]) { a00[i] = p[o00[i]]; a01[i] = p[o01[i]]; a10[i] = p[o10[i]]; a11[i] = p[o11[i]]; }
+            else if (x < W) { a00[i] = q[(size_t)y * im1.pitch + x]; a01[i] = a10[i] = a11[i] = 0; }
+            else { a00[i] = a01[i] = a10[i] = a11[i] = 0; }
+        }
+#pragma unroll
+        for (int i = 0; i < kWarpPix; i++) {
+            const int x = xb + 32 * i;
+            if (x >= W) continue;
+            T acc;
+            if (inside[i]) {
+                acc = 0;
+                acc += a00[i] * w00[i];
+                acc += a01[i] * w01[i];
+                acc += a10[i] * w10[i];
+                acc += a11[i] * w11[i];
+            } else {
+                acc = a00[i];          // Im1 fallback outside the image
+            }
+            warp.ch(k)[(size_t)y * warp.pitch + x] = acc;
+        }
     }
 }
 
