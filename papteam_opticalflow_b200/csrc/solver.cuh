@@ -84,14 +84,16 @@ inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced)
     if (forced > 0) return std::min(forced, nsor);
     double best = 1e300;
     int best_t = 1;
-    for (int t = 1; t <= std::min(nsor, 8); t++) {
+    for (int t = 1; t <= std::min(nsor, 12); t++) {
         SorTiling tx = sor_tiling(w, kSorRegionW, 2 * t), ty = sor_tiling(h, region_h, 2 * t);
         if (tx.ntiles == 0 || ty.ntiles == 0) break;
         double ctas = (double)tx.ntiles * ty.ntiles;
         double waves = std::ceil(ctas / 148.0);
-        double per_cta = 6000.0 + 2.0 * t * 450.0;  // load/store phase + 2t half-sweeps, in clocks
+        // fitted on B200 (tools/sor_sweep.py): a pass costs ~3.8 us of launch/ramp plus, per round of
+        // tiles, ~2.9 us (stage -> registers, write-back, TMA not yet hidden) + ~0.2 us per half-sweep
+        double per_round = 5500.0 + 2.0 * t * 380.0;
         double passes = std::ceil((double)nsor / t);
-        double cost = passes * (waves * per_cta + 4000.0);
+        double cost = passes * (waves * per_round + 7200.0);
         if (cost < best) { best = cost; best_t = t; }
     }
     return best_t;
