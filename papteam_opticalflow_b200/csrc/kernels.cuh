@@ -492,6 +492,32 @@ __global__ void k_bicubic_warp(Img<T> ref, Img<T> im, Img<T> ix, Img<T> iy, Img<
     T dx2 = dx * dx, dy2 = dy * dy, dx3 = dx * dx2, dy3 = dy * dy2;
     size_t corner[4] = {(size_t)y0 * im.pitch + x0, (size_t)y0 * im.pitch + x1,
                         (size_t)y1 * im.pitch + x0, (size_t)y1 * im.pitch + x1};
+    if (sizeof(T) == 4) {
+        // FP32 fast mode: the same bicubic Hermite patch in separable basis form,
+        //   f = sum_{a,b in {0,1}} I_ab hv_a(dx) hv_b(dy) + Ix_ab hd_a(dx) hv_b(dy) + Iy_ab hv_a(dx) hd_b(dy) + Ixy_ab hd_a(dx) hd_b(dy)
+        // with hv_0 = 2t^3-3t^2+1, hv_1 = 3t^2-2t^3, hd_0 = t^3-2t^2+t, hd_1 = t^3-t^2: algebraically the
+        // polynomial the 16 coefficients of S/Image.h:2497-2530 describe (16 FMAs per channel instead of ~150).
+        const T vx0 = 2 * dx3 - 3 * dx2 + 1, vx1 = 3 * dx2 - 2 * dx3, gx0 = dx3 - 2 * dx2 + dx, gx1 = dx3 - dx2;
+        const T vy0 = 2 * dy3 - 3 * dy2 + 1, vy1 = 3 * dy2 - 2 * dy3, gy0 = dy3 - 2 * dy2 + dy, gy1 = dy3 - dy2;
+        // corner index: 0 = (x0,y0), 1 = (x1,y0), 2 = (x0,y1), 3 = (x1,y1)
+        const T bp[4] = {vx0 * vy0, vx1 * vy0, vx0 * vy1, vx1 * vy1};
+        const T bx[4] = {gx0 * vy0, gx1 * vy0, gx0 * vy1, gx1 * vy1};
+        const T by[4] = {vx0 * gy0, vx1 * gy0, vx0 * gy1, vx1 * gy1};
+        const T bz[4] = {gx0 * gy0, gx1 * gy0, gx0 * gy1, gx1 * gy1};
+        for (int k = 0; k < C; k++) {
+            const T *pi = im.ch(k), *px = ix.ch(k), *py = iy.ch(k), *pz = ixy.ch(k);
+            T val = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                val += pi[corner[t]] * bp[t];
+                val += px[corner[t]] * bx[t];
+                val += py[corner[t]] * by[t];
+                val += pz[corner[t]] * bz[t];
+            }
+            o[k] = (double)min(max(val, (T)0), (T)1);
+        }
+        return;
+    }
     for (int k = 0; k < C; k++) {
         T s[16];
         const T* q[4] = {im.ch(k), ix.ch(k), iy.ch(k), ixy.ch(k)};
