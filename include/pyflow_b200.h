@@ -125,6 +125,18 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                   int nSORIterations, int colType, int h, int w, int c, int mode,
                   const int* devices, int ndevices, double* seconds);
 
+/* ---- ONE large pair over several GPUs (BASELINE config 5): every device runs the
+ * cheap stages redundantly, the SOR solve is split into row bands with peer-to-peer halo exchange
+ * over NVLink after every fused-sweep pass (cudaMemcpyPeerAsync ordered by events, no collective).
+ * FP32 red-black mode only; the result is bit-identical to the single-GPU fast mode.  Levels with
+ * fewer than split_min_pixels pixels (<0: default 400000) are solved redundantly.  devices may
+ * repeat an index (bands then share one GPU -- used by the single-GPU tests of the exchange logic).
+ * stats (may be NULL, 4 doubles): solve ms, halo bytes pulled, gather bytes pulled, split solves. */
+int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2,
+                     double alpha, double ratio, int minWidth, int levels, int nOuterFPIterations,
+                     int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,
+                     const int* devices, int ndevices, long long split_min_pixels, double* stats);
+
 /* ---- single stages: the reference's public static functions (S/OpticalFlow.h:28-56) and the
  *      Image/ImageProcessing primitives they use, one call each, for per-stage parity tests.
  *      Same HWC float64 host buffers; `mode` selects the arithmetic (FP64 or FP32). ------------ */

@@ -396,6 +396,22 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     return PF_OK;
 }
 
+int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2, double alpha,
+                     double ratio, int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w,
+                     int c, const int* devices, int ndevices, long long split_min_pixels, double* stats) {
+    return guarded([&]() -> int {
+        if (!vx || !vy || !warpI2 || !im1 || !im2 || !devices || ndevices < 1 || ndevices > 16) return fail(PF_EINVAL, "bad argument");
+        int r;
+        if ((r = check_image(h, w, c))) return r;
+        for (int d = 0; d < ndevices; d++)
+            if ((r = check_device(devices[d]))) return r;
+        if (nOuter < 0 || nInner < 0 || nSOR < 0) return fail(PF_EINVAL, "iteration counts must be non-negative");
+        Params p{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, PF_MODE_FP32_REDBLACK, devices[0]};
+        multigpu_flow_f32(vx, vy, warpI2, im1, im2, p, devices, ndevices, split_min_pixels < 0 ? 400000 : split_min_pixels, stats);
+        return PF_OK;
+    });
+}
+
 // ---- single stages ---------------------------------------------------------------------------------
 int pf_stage_pyramid(double* out, const double* im, int h, int w, int c, double ratio, int levels, int mode, int device) {
     return guarded([&]() -> int {

@@ -21,6 +21,10 @@ struct StageCalls {
                 const double*, const double*, double, int, int, int, int, int, int, double*, double*);
 };
 
+// one pair over several GPUs (row-band split of the SOR solve); FP32 red-black only.
+// stats (4 doubles, may be NULL): solve ms, halo bytes pulled, gather bytes pulled, solves that were split
+void multigpu_flow_f32(double* vx, double* vy, double* warp, const double* im1, const double* im2, const Params& p,
+                       const int* devices, int ndev, long long split_min_pixels, double* stats);
 PlanBase* make_plan_f32(const Params& p);
 PlanBase* make_plan_f64(const Params& p);
 const StageCalls& stages_f32();

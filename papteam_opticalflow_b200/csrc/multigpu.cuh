@@ -1,0 +1,200 @@
+// MultiPlan: ONE frame pair solved by several GPUs (BASELINE config 5, SURVEY.md 8e second row).
+//
+// Every device holds a full replica of the plan and runs the cheap stages (pyramid, features,
+// assembly, warp) redundantly, so those stages need no communication and stay bit-identical to the
+// single-GPU path.  The SOR solve -- ~80 % of the time of a 3840x2160 pair with 60 sweeps -- is split
+// into contiguous ROW BANDS of tile rows: in each fused-sweep pass device g runs the tile kernel only
+// on its band, then pulls the 2*nsw halo rows its next pass will read from the neighbours that own
+// them with peer-to-peer copies over NVLink (cudaMemcpyPeerAsync between peer-enabled devices, ordered
+// by CUDA events; no host synchronisation, no NCCL: this is a nearest-neighbour halo exchange, not a
+// collective).  After the last pass every device gathers the other bands so that the replicated
+// update + warp stage sees the complete du, dv.  The red-black update is independent of the tiling, so
+// the result equals the single-GPU result bit for bit.
+// Levels below `split_min_pixels` are solved redundantly on every device (no exchange at all).
+// The lexicographic parity mode does not band-split (band b would wait for band b-1 in every sweep):
+// replicas only.
+#pragma once
+#include <chrono>
+#include "solver.cuh"
+
+namespace pf {
+
+class MultiPlan {
+  public:
+    MultiPlan(const Params& p, const int* devices, int ndev, long long split_min_pixels)
+        : P(p), split_min_(split_min_pixels) {
+        if (mode_is_lex(p.mode) || mode_is_fp64(p.mode)) throw Error(PF_EUNSUPPORTED, "row-band split needs the fp32_redblack mode");
+        for (int g = 0; g < ndev; g++) devs_.push_back(devices[g]);
+        for (int g = 0; g < ndev; g++) {
+            PF_CUDA(cudaSetDevice(devs_[g]));
+            for (int h = 0; h < ndev; h++) {
+                if (devs_[h] == devs_[g]) continue;
+                int can = 0;
+                PF_CUDA(cudaDeviceCanAccessPeer(&can, devs_[g], devs_[h]));
+                if (can) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(devs_[h], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PF_CUDA(e);
+                    cudaGetLastError();
+                }
+            }
+            Params q = p;
+            q.device = devs_[g];
+            plans_.emplace_back(new Plan<float>(q));
+            cudaEvent_t e1, e2;
+            PF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            PF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            ev_pass_.push_back(e1);
+            ev_gather_.push_back(e2);
+        }
+    }
+    ~MultiPlan() {
+        for (size_t g = 0; g < devs_.size(); g++) {
+            cudaSetDevice(devs_[g]);
+            cudaEventDestroy(ev_pass_[g]);
+            cudaEventDestroy(ev_gather_[g]);
+        }
+    }
+    bool matches(const Params& p, const int* devices, int ndev, long long split_min) const {
+        if ((int)devs_.size() != ndev || split_min != split_min_) return false;
+        for (int g = 0; g < ndev; g++)
+            if (devs_[g] != devices[g]) return false;
+        return P.h == p.h && P.w == p.w && P.c == p.c && P.alpha == p.alpha && P.ratio == p.ratio && P.min_width == p.min_width &&
+               P.levels == p.levels && P.n_outer == p.n_outer && P.n_inner == p.n_inner && P.n_sor == p.n_sor &&
+               P.col_type == p.col_type && P.mode == p.mode;
+    }
+
+    // returns milliseconds of the solve (host clock around device-synchronised region)
+    double execute(double* vx, double* vy, double* warp, const double* im1, const double* im2, double* stats) {
+        const int G = (int)devs_.size();
+        for (int g = 0; g < G; g++) plans_[g]->upload(im1, im2);
+        sync_all();
+        auto t0 = std::chrono::steady_clock::now();
+        solve();
+        sync_all();
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        plans_[0]->download(vx, vy, warp);
+        if (stats) {
+            stats[0] = ms;
+            stats[1] = (double)halo_bytes_;
+            stats[2] = (double)gather_bytes_;
+            stats[3] = (double)split_solves_;
+        }
+        return ms;
+    }
+
+  private:
+    void on(int g) { PF_CUDA(cudaSetDevice(devs_[g])); }
+    void sync_all() {
+        for (size_t g = 0; g < devs_.size(); g++) {
+            on((int)g);
+            PF_CUDA(cudaStreamSynchronize(plans_[g]->stream()));
+        }
+    }
+
+    void solve() {
+        const int G = (int)devs_.size();
+        halo_bytes_ = gather_bytes_ = 0;
+        split_solves_ = 0;
+        gathered_once_ = false;
+        for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_begin(); }
+        const int nlev = plans_[0]->levels();
+        for (int k = nlev - 1; k >= 0; k--) {
+            for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_level(k); }
+            for (int it = 0; it < plans_[0]->n_outer_at(k); it++) {
+                for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_getdxs(k); }
+                for (int hh = 0; hh < P.n_inner; hh++) {
+                    for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_assemble(k, hh); }
+                    sor(k);
+                }
+                for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_update(k); }
+            }
+        }
+        for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_end(); }
+    }
+
+    // rows [r0, r1) of plane `src` on device hs -> same rows of plane `dst` on device hd, on hd's stream
+    void pull_rows(int hd, float* dst, int hs, const float* src, int r0, int r1, int pitch, long long& counter) {
+        if (r1 <= r0) return;
+        size_t off = (size_t)r0 * pitch, bytes = (size_t)(r1 - r0) * pitch * sizeof(float);
+        PF_CUDA(cudaMemcpyPeerAsync(dst + off, devs_[hd], src + off, devs_[hs], bytes, plans_[hd]->stream()));
+        counter += (long long)bytes;
+    }
+
+    void sor(int k) {
+        typedef SorRunner<float> Runner;
+        const int G = (int)devs_.size();
+        const int w = plans_[0]->level_w(k), h = plans_[0]->level_h(k), nsor = plans_[0]->n_sor_at(k);
+        std::vector<Plan<float>::SorView> v;
+        for (int g = 0; g < G; g++) v.push_back(plans_[g]->sor_view());
+        std::vector<Runner::SorPass> sched = v[0].runner->schedule(w, h, nsor);
+        bool split = G > 1 && (long long)w * h >= split_min_ && v[0].runner->use_tma && !v[0].runner->simple_rb && nsor > 0;
+        for (auto& ps : sched)
+            if (ps.ty.ntiles < G) split = false;          // every device needs at least one tile row
+        if (!split) {
+            for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_sor(k); }
+            return;
+        }
+        split_solves_++;
+        const int pitch = v[0].args.pitch;
+        // nobody may overwrite a buffer another device is still gathering from (previous solve)
+        if (gathered_once_)
+            for (int g = 0; g < G; g++) {
+                on(g);
+                for (int o = 0; o < G; o++)
+                    if (o != g) PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_gather_[o], 0));
+            }
+        auto band = [&](const Runner::SorPass& ps, int g, int& tb, int& te) {
+            tb = (int)((long long)g * ps.ty.ntiles / G);
+            te = (int)((long long)(g + 1) * ps.ty.ntiles / G);
+        };
+        for (size_t p = 0; p < sched.size(); p++) {
+            const Runner::SorPass& ps = sched[p];
+            for (int g = 0; g < G; g++) {
+                on(g);
+                int tb, te;
+                band(ps, g, tb, te);
+                v[g].runner->launch_pass(v[g].args, ps, *v[g].du, *v[g].dv, *v[g].du2, *v[g].dv2, tb, te);
+                PF_CUDA(cudaEventRecord(ev_pass_[g], plans_[g]->stream()));
+                std::swap(*v[g].du, *v[g].du2);      // the result of this pass is now in du/dv
+                std::swap(*v[g].dv, *v[g].dv2);
+            }
+            const bool last = p + 1 == sched.size();
+            for (int g = 0; g < G; g++) {
+                on(g);
+                // rows device g needs next: everything for the replicated stages after the last pass,
+                // otherwise exactly the rows its next pass reads
+                int need_lo = 0, need_hi = h;
+                if (!last) {
+                    int tb, te;
+                    band(sched[p + 1], g, tb, te);
+                    need_lo = sched[p + 1].in_lo(tb);
+                    need_hi = sched[p + 1].in_hi(te - 1, h);
+                }
+                for (int o = 0; o < G; o++) {
+                    if (o == g) continue;
+                    int tb, te;
+                    band(ps, o, tb, te);
+                    int r0 = std::max(need_lo, ps.out_lo(tb)), r1 = std::min(need_hi, ps.out_hi(te - 1, h));
+                    if (r1 <= r0) continue;
+                    PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_pass_[o], 0));
+                    long long& ctr = last ? gather_bytes_ : halo_bytes_;
+                    pull_rows(g, *v[g].du, o, *v[o].du, r0, r1, pitch, ctr);
+                    pull_rows(g, *v[g].dv, o, *v[o].dv, r0, r1, pitch, ctr);
+                }
+                if (last) PF_CUDA(cudaEventRecord(ev_gather_[g], plans_[g]->stream()));
+            }
+        }
+        gathered_once_ = true;
+    }
+
+    Params P;
+    long long split_min_;
+    std::vector<int> devs_;
+    std::vector<std::unique_ptr<Plan<float>>> plans_;
+    std::vector<cudaEvent_t> ev_pass_, ev_gather_;
+    long long halo_bytes_ = 0, gather_bytes_ = 0;
+    int split_solves_ = 0;
+    bool gathered_once_ = false;
+};
+
+}  // namespace pf

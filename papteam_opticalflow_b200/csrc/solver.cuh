@@ -147,6 +147,71 @@ struct SorRunner {
         }
     }
 
+    // one launch of the tile kernel: sweeps fused, whether it reads du/dv, and its tiling
+    struct SorPass {
+        int nsw;
+        bool has_input;
+        SorTiling tx, ty;
+        // exact output rows of tile row t, and the rows its region reads
+        int out_lo(int t) const { return t > 0 ? t * ty.step + 2 * nsw : 0; }
+        int out_hi(int t, int h) const { return (t * ty.step + kRegionH >= h) ? h : t * ty.step + kRegionH - 2 * nsw; }
+        int in_lo(int t) const { return std::max(0, t * ty.step - 1); }
+        int in_hi(int t, int h) const { return std::min(h, t * ty.step + kRegionH); }
+    };
+
+    std::vector<SorPass> schedule(int w, int h, int nsor) const {
+        std::vector<SorPass> v;
+        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse);
+        for (int done = 0; done < nsor;) {
+            SorPass ps;
+            ps.nsw = std::min(fuse, nsor - done);
+            ps.has_input = done > 0;
+            ps.tx = sor_tiling(w, kSorRegionW, 2 * ps.nsw);
+            ps.ty = sor_tiling(h, kRegionH, 2 * ps.nsw);
+            if (ps.tx.ntiles == 0 || ps.ty.ntiles == 0) throw Error(PF_EINVAL, "SOR tiling failed");
+            v.push_back(ps);
+            done += ps.nsw;
+        }
+        return v;
+    }
+
+    // tile rows [ty_begin, ty_end) of one pass: reads du/dv (if has_input), writes du2/dv2
+    void launch_pass(SorArgs<T> a, const SorPass& ps, T* du, T* dv, T* du2, T* dv2, int ty_begin, int ty_end) {
+        const int w = a.w, h = a.h, nrows = ty_end - ty_begin;
+        if (nrows <= 0) return;
+        a.du_in = ps.has_input ? du : nullptr; a.dv_in = ps.has_input ? dv : nullptr; a.du = du2; a.dv = dv2;
+        if (use_tma) {
+            // persistent, TMA-staged variant: one CTA per SM walks the tiles round-robin
+            SorMaps m;
+            m.phi = make_plane_map(a.phi, w, h, a.pitch, 72, kRegionH + 1);
+            m.dxy = make_plane_map(a.dxy, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.iu = make_plane_map(a.iu, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.iv = make_plane_map(a.iv, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.bu = make_plane_map(a.bu, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.bv = make_plane_map(a.bv, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.du = make_plane_map(ps.has_input ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
+            m.dv = make_plane_map(ps.has_input ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
+            int ntiles = ps.tx.ntiles * nrows;
+            size_t smem = sor_smem_bytes();
+            bool launched = false;
+            if constexpr (!kF64 && kR == 4) {
+                if (packed) {
+                    k_sor_rb_tma_pk<kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+                        m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
+                        ps.tx.step, ps.ty.step, ty_begin);
+                    launched = true;
+                }
+            }
+            if (!launched)
+                k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+                    m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
+                    ps.tx.step, ps.ty.step, ty_begin);
+        } else {
+            if (ty_begin != 0 || ty_end != ps.ty.ntiles) throw Error(PF_EUNSUPPORTED, "row-band split needs the TMA SOR kernel");
+            k_sor_rb_tile<T, kR, kNW><<<dim3(ps.tx.ntiles, ps.ty.ntiles), kNW * 32, 0, st>>>(a, ps.nsw, ps.tx.step, ps.ty.step);
+        }
+    }
+
     // returns the number of kernel launches
     int run(SorArgs<T> a, T*& du, T*& dv, T*& du2, T*& dv2, int nsor) {
         const int w = a.w, h = a.h;
@@ -174,43 +239,11 @@ struct SorRunner {
                 }
             return launches;
         }
-        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse);
-        int done = 0;
-        while (done < nsor) {
-            int nsw = std::min(fuse, nsor - done);
-            SorTiling tx = sor_tiling(w, kSorRegionW, 2 * nsw), ty = sor_tiling(h, kRegionH, 2 * nsw);
-            if (tx.ntiles == 0 || ty.ntiles == 0) throw Error(PF_EINVAL, "SOR tiling failed");
-            a.du_in = done ? du : nullptr; a.dv_in = done ? dv : nullptr; a.du = du2; a.dv = dv2;
-            if (use_tma) {
-                // persistent, TMA-staged variant: one CTA per SM walks the tiles round-robin
-                SorMaps m;
-                m.phi = make_plane_map(a.phi, w, h, a.pitch, 72, kRegionH + 1);
-                m.dxy = make_plane_map(a.dxy, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.iu = make_plane_map(a.iu, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.iv = make_plane_map(a.iv, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.bu = make_plane_map(a.bu, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.bv = make_plane_map(a.bv, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.du = make_plane_map(done ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
-                m.dv = make_plane_map(done ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
-                int ntiles = tx.ntiles * ty.ntiles;
-                size_t smem = sor_smem_bytes();
-                bool launched = false;
-                if constexpr (!kF64 && kR == 4) {
-                    if (packed) {
-                        k_sor_rb_tma_pk<kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
-                            m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, nsw, done ? 1 : 0, tx.ntiles, ty.ntiles, tx.step, ty.step);
-                        launched = true;
-                    }
-                }
-                if (!launched)
-                k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
-                    m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, nsw, done ? 1 : 0, tx.ntiles, ty.ntiles, tx.step, ty.step);
-            } else
-            k_sor_rb_tile<T, kR, kNW><<<dim3(tx.ntiles, ty.ntiles), kNW * 32, 0, st>>>(a, nsw, tx.step, ty.step);
+        for (const SorPass& ps : schedule(w, h, nsor)) {
+            launch_pass(a, ps, du, dv, du2, dv2, 0, ps.ty.ntiles);
             launches++;
             std::swap(du, du2);
             std::swap(dv, dv2);
-            done += nsw;
         }
         return launches;
     }
@@ -496,16 +529,36 @@ class Plan : public PlanBase {
     }
 
     // ---- the whole solve on st_ ------------------------------------------------------------------
-    void enqueue_solve() {
+    // ---- the whole solve on st_, as phases so that several plans (one per GPU) can be driven in
+    //      lock step by MultiPlan (multigpu.cuh) ---------------------------------------------------
+    struct Ctx {
+        Taps<T> d5, g5, d3;
+        T eps;
+        T *du_e, *dv_e, *du2_e, *dv2_e, *u_e, *v_e, *u2_e, *v2_e;   // pointer roles on entry
+        int pw, ph;                                                   // previous (coarser) level size
+        int w, h, pitch;                                              // current level
+        Img<T> f1, f2, wf, s1, s2, tmp, blend, imdx, imdy, imdt;
+        FusedMaps fmaps;
+    };
+    Ctx cx_;
+
+  public:
+    int n_outer_at(int k) const { return P.n_outer + k; }
+    int n_sor_at(int k) const { return P.n_sor + 3 * k; }
+    int level_w(int k) const { return geo_[k].w; }
+    int level_h(int k) const { return geo_[k].h; }
+
+    // -- Construction: import + both pyramids (S/GaussianPyramid.cpp:79-108) --
+    void ph_begin() {
         const double d5raw[5] = {1.0 / 12, -8.0 / 12, 0.0 / 12, 8.0 / 12, -1.0 / 12};
         const double g5raw[5] = {0.02, 0.11, 0.74, 0.11, 0.02};
         const double d3raw[3] = {-0.5, 0, 0.5};
-        const Taps<T> d5 = make_taps<T>(d5raw, 2), g5 = make_taps<T>(g5raw, 2), d3 = make_taps<T>(d3raw, 1);
-        const T eps = (T)std::pow(0.001, 2);
-        T* du_entry = du_; T* dv_entry = dv_; T* du2_entry = du2_; T* dv2_entry = dv2_;
-        T* u_entry = u_; T* v_entry = v_; T* u2_entry = u2_; T* v2_entry = v2_;
-
-        // -- Construction: import + both pyramids (S/GaussianPyramid.cpp:79-108) --
+        Ctx& c = cx_;
+        c.d5 = make_taps<T>(d5raw, 2); c.g5 = make_taps<T>(g5raw, 2); c.d3 = make_taps<T>(d3raw, 1);
+        c.eps = (T)std::pow(0.001, 2);
+        c.du_e = du_; c.dv_e = dv_; c.du2_e = du2_; c.dv2_e = dv2_;
+        c.u_e = u_; c.v_e = v_; c.u2_e = u2_; c.v2_e = v2_;
+        c.pw = c.ph = 0;
         set_phase(PF_T_CONSTRUCTION, 0);
         k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in1_, pyr1_[0]);
         k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in2_, pyr2_[0]);
@@ -530,141 +583,185 @@ class Plan : public PlanBase {
             for (int i = 0; i < 64; i++) lap0[i] = 0.02;   // S/OpticalFlow.cpp:773-775
             PF_CUDA(cudaMemcpyAsync(d_lap_, lap0, sizeof(lap0), cudaMemcpyHostToDevice, st_));
         }
+    }
 
-        int pw = 0, ph = 0;
-        for (int k = nlev_ - 1; k >= 0; k--) {
-            const int w = geo_[k].w, h = geo_[k].h, pitch = pitch_for(w);
-            const size_t plane_bytes = plane_for(w, h) * sizeof(T);
-            // -- Allocation: features, flow upsampling, warp (S/OpticalFlow.cpp:790-818) --
-            set_phase(PF_T_ALLOCATION, k);
-            Img<T> f1 = view(f1_, w, h, fc_), f2 = view(f2_, w, h, fc_), wf = view(wf_, w, h, fc_);
-            Img<T> s1 = view(s1_, w, h, fc_), s2 = view(s2_, w, h, fc_), tmp = view(tmp_, w, h, fc_);
-            Img<T> blend = view(blend_, w, h, fc_), imdx = view(imdx_, w, h, fc_);
-            Img<T> imdy = view(imdy_, w, h, fc_), imdt = view(imdt_, w, h, fc_);
-            if (P.c == 1 || P.c == 3) {
-                int swap = (k == 0 && P.col_type == 1) ? 1 : 0;
-                k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr1_[k], f1, d5, swap);
-                k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr2_[k], f2, d5, swap);
-            } else {
-                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr1_[k], f1);
-                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr2_[k], f2);
-            }
-            launches_ += 2;
-            if (k == nlev_ - 1) {
-                PF_CUDA(cudaMemsetAsync(u_, 0, plane_bytes, st_));
-                PF_CUDA(cudaMemsetAsync(v_, 0, plane_bytes, st_));
-                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(f2, wf);
-                launches_++;
-            } else {
-                Img<T> su = view(u_, pw, ph, 1), sv = view(v_, pw, ph, 1);
-                Img<T> du = view(u2_, w, h, 1), dv = view(v2_, w, h, 1);
-                double rx = (double)w / pw, ry = (double)h / ph;
-                T scale = (T)(1 / P.ratio);
-                k_resize<T><<<grid2(w, h), 128, 0, st_>>>(su, du, rx, ry, scale, 1);
-                k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
-                std::swap(u_, u2_);
-                std::swap(v_, v2_);
-                k_update_warp<T><<<dim3(ceil_div(w, 128 * kWarpPix), h), 128, 0, st_>>>(f1, f2, wf, u_, v_, nullptr, nullptr, pitch);
-                launches_ += 3;
-            }
-            // Im1 is constant within a level: its smoothed copy is computed once instead of every
-            // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
-            set_phase(PF_T_PHASE1_GENERATE, k);
-            filter_hv(f1, s1, g5, g5);
-
-            FusedMaps fmaps;
-            if (fused_ && fused_tma_) {
-                fmaps.wf = make_image_map(wf.p, w, h, fc_, wf.pitch, wf.plane, 72, kFTY + 8);
-                fmaps.s1 = make_image_map(s1.p, w, h, fc_, s1.pitch, s1.plane, 72, kFTY + 4);
-            }
-            const int n_outer = P.n_outer + k, n_sor = P.n_sor + 3 * k;
-            for (int it = 0; it < n_outer; it++) {
-                if (!fused_) {
-                    // -- Phase1: getDxs (S/OpticalFlow.cpp:80-122), one kernel per reference step --
-                    set_phase(PF_T_PHASE1_GENERATE, k);
-                    filter_h(wf, tmp, g5);
-                    filter_v(tmp, s2, g5);
-                    k_blend_dt<T><<<grid2(w, h, fc_), 128, 0, st_>>>(s1, s2, blend, imdt);
-                    launches_++;
-                    filter_h(blend, imdx, d5);
-                    filter_v(blend, imdy, d5);
-                }
-                for (int hh = 0; hh < P.n_inner; hh++) {
-                    const T* cdu = hh > 0 ? du_ : nullptr;
-                    const T* cdv = hh > 0 ? dv_ : nullptr;
-                    if (fused_) {
-                        // -- Phases 1-4 in one pass over the level (k_fused_assemble) --
-                        set_phase(PF_T_PHASE4_SYSTEM, k);
-                        FusedArgs<T> fa;
-                        fa.s1 = s1; fa.wf = wf;
-                        fa.u = u_; fa.v = v_; fa.du = cdu; fa.dv = cdv;
-                        fa.lap = (kF64 && lex_) ? d_lap_ : nullptr;
-                        fa.phi = phi_; fa.dxy = dxy_; fa.iu = iu_; fa.iv = iv_; fa.bu = bu_; fa.bv = bv_;
-                        fa.w = w; fa.h = h; fa.pitch = pitch;
-                        fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = eps;
-                        fa.g5 = g5; fa.d5 = d5;
-                        if (fused_tma_) {
-                            size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
-                            k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(fmaps, fa);
-                        } else
-                        k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
-                        launches_++;
-                    } else {
-                        // -- Phase2: flow derivatives + phi --
-                        set_phase(PF_T_PHASE2_DERIVS, k);
-                        k_phi<T><<<grid2(w, h), 128, 0, st_>>>(u_, v_, cdu, cdv, phi_, w, h, pitch, eps);
-                        launches_++;
-                        // -- Phase3+4: psi, products, Laplacian, rhs --
-                        set_phase(PF_T_PHASE4_SYSTEM, k);
-                        AssembleArgs<T> a;
-                        a.imdx = imdx; a.imdy = imdy; a.imdt = imdt;
-                        a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
-                        a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
-                        a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
-                        a.dx2 = nullptr; a.dy2 = nullptr;
-                        a.w = w; a.h = h; a.pitch = pitch;
-                        a.alpha = (T)P.alpha; a.omega = (T)1.8; a.eps = eps;
-                        k_assemble<T><<<grid2(w, h), 128, 0, st_>>>(a);
-                        launches_++;
-                    }
-                    // -- Phase5: SOR --
-                    set_phase(PF_T_PHASE5_SOR, k);
-                    run_sor(w, h, pitch, n_sor, k);
-                }
-                // -- Phase6: update + warp (+ noise estimate in the parity mode) --
-                set_phase(PF_T_PHASE6_UPDATE, k);
-                k_update_warp<T><<<dim3(ceil_div(w, 128 * kWarpPix), h), 128, 0, st_>>>(f1, f2, wf, u_, v_, du_, dv_, pitch);
-                launches_++;
-                if (kF64 && lex_) {
-                    k_noise_accum<T><<<dim3(std::min(8, ceil_div(w, 128)), std::min(h, 64), fc_), 128, 0, st_>>>(f1, wf, d_acc_);
-                    k_noise_final<<<1, 32, 0, st_>>>(d_acc_, d_lap_, fc_);
-                    launches_ += 2;
-                }
-            }
-            pw = w;
-            ph = h;
+    // -- Allocation: features, flow upsampling, warp (S/OpticalFlow.cpp:790-818); smoothed Im1 --
+    void ph_level(int k) {
+        Ctx& c = cx_;
+        const int w = geo_[k].w, h = geo_[k].h, pitch = pitch_for(w);
+        c.w = w; c.h = h; c.pitch = pitch;
+        const size_t plane_bytes = plane_for(w, h) * sizeof(T);
+        set_phase(PF_T_ALLOCATION, k);
+        c.f1 = view(f1_, w, h, fc_); c.f2 = view(f2_, w, h, fc_); c.wf = view(wf_, w, h, fc_);
+        c.s1 = view(s1_, w, h, fc_); c.s2 = view(s2_, w, h, fc_); c.tmp = view(tmp_, w, h, fc_);
+        c.blend = view(blend_, w, h, fc_); c.imdx = view(imdx_, w, h, fc_);
+        c.imdy = view(imdy_, w, h, fc_); c.imdt = view(imdt_, w, h, fc_);
+        if (P.c == 1 || P.c == 3) {
+            int swap = (k == 0 && P.col_type == 1) ? 1 : 0;
+            k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr1_[k], c.f1, c.d5, swap);
+            k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr2_[k], c.f2, c.d5, swap);
+        } else {
+            k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr1_[k], c.f1);
+            k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr2_[k], c.f2);
         }
-        // -- PostProcessing: bicubic warp of the original frame + clamp; export the flow --
-        set_phase(PF_T_POST, 0);
-        {
-            const Img<T>& im1 = pyr1_[0];
-            const Img<T>& im2 = pyr2_[0];
-            Img<T> ix = view(b_ix_, P.w, P.h, P.c), iy = view(b_iy_, P.w, P.h, P.c), ixy = view(b_ixy_, P.w, P.h, P.c);
-            const double one[1] = {1.0};
-            const Taps<T> id = make_taps<T>(one, 0);
-            filter_hv(im2, ix, d3, id);
-            filter_hv(im2, iy, id, d3);
-            filter_hv(im2, ixy, d3, d3);
-            k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, d_warp_);
-            Img<T> uo = view(u_, P.w, P.h, 1), vo = view(v_, P.w, P.h, 1);
-            k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
-            k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(vo, d_vy_);
+        launches_ += 2;
+        if (k == nlev_ - 1) {
+            PF_CUDA(cudaMemsetAsync(u_, 0, plane_bytes, st_));
+            PF_CUDA(cudaMemsetAsync(v_, 0, plane_bytes, st_));
+            k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(c.f2, c.wf);
+            launches_++;
+        } else {
+            Img<T> su = view(u_, c.pw, c.ph, 1), sv = view(v_, c.pw, c.ph, 1);
+            Img<T> du = view(u2_, w, h, 1), dv = view(v2_, w, h, 1);
+            double rx = (double)w / c.pw, ry = (double)h / c.ph;
+            T scale = (T)(1 / P.ratio);
+            k_resize<T><<<grid2(w, h), 128, 0, st_>>>(su, du, rx, ry, scale, 1);
+            k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
+            std::swap(u_, u2_);
+            std::swap(v_, v2_);
+            k_update_warp<T><<<dim3(ceil_div(w, 128 * kWarpPix), h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
             launches_ += 3;
         }
+        // Im1 is constant within a level: its smoothed copy is computed once instead of every
+        // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
+        set_phase(PF_T_PHASE1_GENERATE, k);
+        filter_hv(c.f1, c.s1, c.g5, c.g5);
+        if (fused_ && fused_tma_) {
+            c.fmaps.wf = make_image_map(c.wf.p, w, h, fc_, c.wf.pitch, c.wf.plane, 72, kFTY + 8);
+            c.fmaps.s1 = make_image_map(c.s1.p, w, h, fc_, c.s1.pitch, c.s1.plane, 72, kFTY + 4);
+        }
+        c.pw = w;
+        c.ph = h;
+    }
+
+    // -- Phase1 (un-fused path only): getDxs (S/OpticalFlow.cpp:80-122), one kernel per reference step --
+    void ph_getdxs(int k) {
+        if (fused_) return;
+        Ctx& c = cx_;
+        set_phase(PF_T_PHASE1_GENERATE, k);
+        filter_h(c.wf, c.tmp, c.g5);
+        filter_v(c.tmp, c.s2, c.g5);
+        k_blend_dt<T><<<grid2(c.w, c.h, fc_), 128, 0, st_>>>(c.s1, c.s2, c.blend, c.imdt);
+        launches_++;
+        filter_h(c.blend, c.imdx, c.d5);
+        filter_v(c.blend, c.imdy, c.d5);
+    }
+
+    // -- Phases 1-4 of inner iteration hh: the linear system of S/OpticalFlow.cpp:295-448 --
+    void ph_assemble(int k, int hh) {
+        Ctx& c = cx_;
+        const int w = c.w, h = c.h, pitch = c.pitch;
+        const T* cdu = hh > 0 ? du_ : nullptr;
+        const T* cdv = hh > 0 ? dv_ : nullptr;
+        if (fused_) {
+            set_phase(PF_T_PHASE4_SYSTEM, k);
+            FusedArgs<T> fa;
+            fa.s1 = c.s1; fa.wf = c.wf;
+            fa.u = u_; fa.v = v_; fa.du = cdu; fa.dv = cdv;
+            fa.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+            fa.phi = phi_; fa.dxy = dxy_; fa.iu = iu_; fa.iv = iv_; fa.bu = bu_; fa.bv = bv_;
+            fa.w = w; fa.h = h; fa.pitch = pitch;
+            fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = c.eps;
+            fa.g5 = c.g5; fa.d5 = c.d5;
+            if (fused_tma_) {
+                size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
+                k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
+            } else {
+                k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
+            }
+            launches_++;
+        } else {
+            set_phase(PF_T_PHASE2_DERIVS, k);
+            k_phi<T><<<grid2(w, h), 128, 0, st_>>>(u_, v_, cdu, cdv, phi_, w, h, pitch, c.eps);
+            launches_++;
+            set_phase(PF_T_PHASE4_SYSTEM, k);
+            AssembleArgs<T> a;
+            a.imdx = c.imdx; a.imdy = c.imdy; a.imdt = c.imdt;
+            a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
+            a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+            a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
+            a.dx2 = nullptr; a.dy2 = nullptr;
+            a.w = w; a.h = h; a.pitch = pitch;
+            a.alpha = (T)P.alpha; a.omega = (T)1.8; a.eps = c.eps;
+            k_assemble<T><<<grid2(w, h), 128, 0, st_>>>(a);
+            launches_++;
+        }
+    }
+
+    // -- Phase5: SOR on this device alone --
+    void ph_sor(int k) {
+        set_phase(PF_T_PHASE5_SOR, k);
+        run_sor(cx_.w, cx_.h, cx_.pitch, n_sor_at(k), k);
+    }
+
+    // -- Phase6: update + warp (+ noise estimate in the parity mode) --
+    void ph_update(int k) {
+        Ctx& c = cx_;
+        set_phase(PF_T_PHASE6_UPDATE, k);
+        k_update_warp<T><<<dim3(ceil_div(c.w, 128 * kWarpPix), c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
+        launches_++;
+        if (kF64 && lex_) {
+            k_noise_accum<T><<<dim3(std::min(8, ceil_div(c.w, 128)), std::min(c.h, 64), fc_), 128, 0, st_>>>(c.f1, c.wf, d_acc_);
+            k_noise_final<<<1, 32, 0, st_>>>(d_acc_, d_lap_, fc_);
+            launches_ += 2;
+        }
+    }
+
+    // -- PostProcessing: bicubic warp of the original frame + clamp; export the flow --
+    void ph_end() {
+        Ctx& c = cx_;
+        set_phase(PF_T_POST, 0);
+        const Img<T>& im1 = pyr1_[0];
+        const Img<T>& im2 = pyr2_[0];
+        Img<T> ix = view(b_ix_, P.w, P.h, P.c), iy = view(b_iy_, P.w, P.h, P.c), ixy = view(b_ixy_, P.w, P.h, P.c);
+        const double one[1] = {1.0};
+        const Taps<T> id = make_taps<T>(one, 0);
+        filter_hv(im2, ix, c.d3, id);
+        filter_hv(im2, iy, id, c.d3);
+        filter_hv(im2, ixy, c.d3, c.d3);
+        k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, d_warp_);
+        Img<T> uo = view(u_, P.w, P.h, 1), vo = view(v_, P.w, P.h, 1);
+        k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
+        k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(vo, d_vy_);
+        launches_ += 3;
         PF_CHECK_LAUNCH();
         // restore the pointer roles so that a captured graph and a later eager run agree
-        du_ = du_entry; dv_ = dv_entry; du2_ = du2_entry; dv2_ = dv2_entry;
-        u_ = u_entry; v_ = v_entry; u2_ = u2_entry; v2_ = v2_entry;
+        du_ = c.du_e; dv_ = c.dv_e; du2_ = c.du2_e; dv2_ = c.dv2_e;
+        u_ = c.u_e; v_ = c.v_e; u2_ = c.u2_e; v2_ = c.v2_e;
+    }
+
+    // buffers the cooperative (row-band) SOR of MultiPlan works on
+    struct SorView {
+        SorArgs<T> args;
+        T **du, **dv, **du2, **dv2;
+        SorRunner<T>* runner;
+    };
+    SorView sor_view() {
+        SorView v;
+        v.args.phi = phi_; v.args.dxy = dxy_; v.args.iu = iu_; v.args.iv = iv_; v.args.bu = bu_; v.args.bv = bv_;
+        v.args.du = nullptr; v.args.dv = nullptr; v.args.du_in = nullptr; v.args.dv_in = nullptr;
+        v.args.w = cx_.w; v.args.h = cx_.h; v.args.pitch = cx_.pitch;
+        v.args.alpha = (T)P.alpha; v.args.omega = (T)1.8;
+        v.du = &du_; v.dv = &dv_; v.du2 = &du2_; v.dv2 = &dv2_;
+        v.runner = &sor_;
+        return v;
+    }
+
+  private:
+    void enqueue_solve() {
+        ph_begin();
+        for (int k = nlev_ - 1; k >= 0; k--) {
+            ph_level(k);
+            for (int it = 0; it < n_outer_at(k); it++) {
+                ph_getdxs(k);
+                for (int hh = 0; hh < P.n_inner; hh++) {
+                    ph_assemble(k, hh);
+                    ph_sor(k);
+                }
+                ph_update(k);
+            }
+        }
+        ph_end();
     }
 
   public:

@@ -307,7 +307,7 @@ struct SorStage {
 template <typename T, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
-             T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y) {
+             T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0) {
     static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
     typedef typename Vec2<T>::type V2;
     typedef SorStage<T, R, NW> Stage;
@@ -329,7 +329,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
     const T one_m = (T)1 - omega;
 
     auto issue = [&](int tile) {
-        const int tx = tile % ntx, ty = tile / ntx;
+        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;
         mbar_expect_tx(&full_bar, stage_bytes);
         tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
@@ -354,7 +354,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
     uint32_t parity = 0;
 
     for (; tile < ntiles; tile += gridDim.x) {
-        const int tx = tile % ntx, ty = tile / ntx;
+        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;   // even by construction
         const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
 
@@ -489,7 +489,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out, float* __restrict__ dv_out, int W, int H,
-                int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y) {
+                int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0) {
     constexpr int R = 4, RH = NW * R;
     typedef SorStage<float, R, NW> Stage;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -504,7 +504,7 @@ k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out
     const float2 one_m2 = make_float2(1.0f - omega, 1.0f - omega);
 
     auto issue = [&](int tile) {
-        const int tx = tile % ntx, ty = tile / ntx;
+        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;
         mbar_expect_tx(&full_bar, stage_bytes);
         tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
@@ -528,7 +528,7 @@ k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out
     uint32_t parity = 0;
 
     for (; tile < ntiles; tile += gridDim.x) {
-        const int tx = tile % ntx, ty = tile / ntx;
+        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;   // multiples of 4
         const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
 

@@ -212,6 +212,30 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
     return vx, vy, wi
 
 
+def coarse2fine_flow_multigpu(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,
+                              nInnerFPIterations=1, nSORIterations=30, colType=0, levels=0, devices=None,
+                              split_min_pixels=-1):
+    """ONE pair solved by several GPUs: the SOR solve of the fine levels is split into row bands with
+    NVLink peer-to-peer halo exchange (pf_multigpu_flow; FP32 red-black mode, bit-identical to the
+    single-GPU fast mode).  Returns (u, v, im2W, stats) with stats = dict(ms, halo_bytes, gather_bytes,
+    split_solves)."""
+    L = _lib.lib()
+    _check_image("Im1", im1)
+    _check_image("Im2", im2)
+    if im1.shape != im2.shape:
+        raise ValueError("Im1 and Im2 must have the same shape")
+    if devices is None:
+        devices = list(range(max(1, L.pf_device_count())))
+    h, w, c = im1.shape
+    vx, vy, wi = np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))
+    dev = (C.c_int * len(devices))(*devices)
+    st = np.zeros(4)
+    check(L.pf_multigpu_flow(_ptr(vx), _ptr(vy), _ptr(wi), _ptr(im1), _ptr(im2), float(alpha), float(ratio), int(minWidth),
+                             int(levels), int(nOuterFPIterations), int(nInnerFPIterations), int(nSORIterations),
+                             int(colType), h, w, c, dev, len(devices), int(split_min_pixels), _ptr(st)))
+    return vx, vy, wi, dict(ms=st[0], halo_bytes=int(st[1]), gather_bytes=int(st[2]), split_solves=int(st[3]))
+
+
 def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,
                            nInnerFPIterations=1, nSORIterations=30, colType=0, levels=0, mode=None,
                            devices=None, outs=None):

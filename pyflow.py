@@ -1,4 +1,5 @@
 """`import pyflow` drop-in: same module and function name as the reference's Cython extension
 (Par/pyflow.pyx), backed by the B200 CUDA library.  See papteam_opticalflow_b200/pyflow.py."""
 from papteam_opticalflow_b200.pyflow import *  # noqa: F401,F403
-from papteam_opticalflow_b200.pyflow import coarse2fine_flow, coarse2fine_flow_batch, multi_solve, FlowPlan, MODES  # noqa: F401
+from papteam_opticalflow_b200.pyflow import (coarse2fine_flow, coarse2fine_flow_batch, coarse2fine_flow_multigpu,  # noqa: F401
+                                             multi_solve, FlowPlan, MODES)

@@ -286,3 +286,33 @@ def test_config5_4k_gray_sor60_both_modes_vs_reference_golden():
     ul, vl, _ = pyflow.coarse2fine_flow(im1, im2, *args, mode="fp32_wavefront")
     el = epe(ul, vl, pu, pv)
     assert el.mean() <= 1e-4 and el.max() <= 0.5
+
+
+@pytest.mark.parametrize("nbands", [2, 3, 5])
+def test_row_band_split_equals_single_gpu(nbands):
+    """SURVEY 8e / BASELINE config 5 mechanism: one pair, SOR split into row bands with halo pulls
+    after every fused-sweep pass and a gather after the last one.  With a repeated device index the
+    bands share this GPU (same code path: per-band launches, event-ordered cudaMemcpyPeerAsync), so the
+    exchange logic is tested without a second device.  The red-black update does not depend on the
+    tiling, hence the result must be BIT-IDENTICAL to the single-GPU fast mode."""
+    a, b = load_frame(480, 1), load_frame(480, 2)
+    u0, v0, w0 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=[0] * nbands, split_min_pixels=20000)
+    assert st["split_solves"] > 0 and st["halo_bytes"] > 0 and st["gather_bytes"] > 0
+    assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+    # below the threshold every band solves redundantly: no exchange at all, same result
+    u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=[0] * nbands, split_min_pixels=10 ** 9)
+    assert st["split_solves"] == 0 and st["halo_bytes"] == 0
+    assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+
+
+def test_row_band_split_on_real_peers_if_present():
+    from papteam_opticalflow_b200 import _lib
+    n = _lib.lib().pf_device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs (validated separately with gpurun --gpus 2, see DESIGN.md)")
+    a, b = load_frame(960, 1), load_frame(960, 2)
+    u0, v0, w0 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=list(range(min(n, 4))), split_min_pixels=50000)
+    assert st["split_solves"] > 0
+    assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
