@@ -129,7 +129,7 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
  * cheap stages redundantly, the SOR solve is split into row bands with peer-to-peer halo exchange
  * over NVLink after every fused-sweep pass (cudaMemcpyPeerAsync ordered by events, no collective).
  * FP32 red-black mode only; the result is bit-identical to the single-GPU fast mode.  Levels with
- * fewer than split_min_pixels pixels (<0: default 400000) are solved redundantly.  devices may
+ * fewer than split_min_pixels pixels (<0: default 2000000) are solved redundantly.  devices may
  * repeat an index (bands then share one GPU -- used by the single-GPU tests of the exchange logic).
  * stats (may be NULL, 4 doubles): solve ms, halo bytes pulled, gather bytes pulled, split solves. */
 int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2,

@@ -407,7 +407,7 @@ int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, 
             if ((r = check_device(devices[d]))) return r;
         if (nOuter < 0 || nInner < 0 || nSOR < 0) return fail(PF_EINVAL, "iteration counts must be non-negative");
         Params p{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, PF_MODE_FP32_REDBLACK, devices[0]};
-        multigpu_flow_f32(vx, vy, warpI2, im1, im2, p, devices, ndevices, split_min_pixels < 0 ? 400000 : split_min_pixels, stats);
+        multigpu_flow_f32(vx, vy, warpI2, im1, im2, p, devices, ndevices, split_min_pixels < 0 ? 2000000 : split_min_pixels, stats);
         return PF_OK;
     });
 }

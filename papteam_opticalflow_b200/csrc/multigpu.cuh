@@ -23,6 +23,8 @@ class MultiPlan {
   public:
     MultiPlan(const Params& p, const int* devices, int ndev, long long split_min_pixels)
         : P(p), split_min_(split_min_pixels) {
+        const char* e = getenv("PF_MULTI_PULL");
+        push_ = !(e && atoi(e));
         if (mode_is_lex(p.mode) || mode_is_fp64(p.mode)) throw Error(PF_EUNSUPPORTED, "row-band split needs the fp32_redblack mode");
         for (int g = 0; g < ndev; g++) devs_.push_back(devices[g]);
         for (int g = 0; g < ndev; g++) {
@@ -46,8 +48,13 @@ class MultiPlan {
             ev_pass_.push_back(e1);
             ev_gather_.push_back(e2);
         }
+        PF_CUDA(cudaSetDevice(devs_[0]));
+        PF_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     }
     ~MultiPlan() {
+        if (gexec_) cudaGraphExecDestroy(gexec_);
+        if (graph_) cudaGraphDestroy(graph_);
+        if (ev_fork_) cudaEventDestroy(ev_fork_);
         for (size_t g = 0; g < devs_.size(); g++) {
             cudaSetDevice(devs_[g]);
             cudaEventDestroy(ev_pass_[g]);
@@ -69,7 +76,7 @@ class MultiPlan {
         for (int g = 0; g < G; g++) plans_[g]->upload(im1, im2);
         sync_all();
         auto t0 = std::chrono::steady_clock::now();
-        solve();
+        run_solve();
         sync_all();
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         plans_[0]->download(vx, vy, warp);
@@ -84,6 +91,53 @@ class MultiPlan {
 
   private:
     void on(int g) { PF_CUDA(cudaSetDevice(devs_[g])); }
+
+    // The launch sequence of all devices (kernels, peer copies, cross-device event edges) is captured
+    // once into ONE multi-device CUDA graph: device 0's stream is the origin, the other streams fork
+    // from it and join back, so a replay needs no host thread in the loop (an eager solve issues
+    // ~10^4 API calls from one thread, which is what bounds a 2-GPU solve otherwise).
+    void run_solve() {
+        const int G = (int)devs_.size();
+        const char* e = getenv("PF_NO_GRAPH");
+        if (e && atoi(e)) { solve(); return; }
+        cudaStream_t s0 = plans_[0]->stream();
+        if (!gexec_ && !graph_failed_) {
+            on(0);
+            cudaError_t st = cudaStreamBeginCapture(s0, cudaStreamCaptureModeGlobal);
+            if (st == cudaSuccess) {
+                try {
+                    PF_CUDA(cudaEventRecord(ev_fork_, s0));
+                    for (int g = 1; g < G; g++) { on(g); PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_fork_, 0)); }
+                    solve();
+                    for (int g = 1; g < G; g++) {
+                        on(g);
+                        PF_CUDA(cudaEventRecord(ev_pass_[g], plans_[g]->stream()));
+                        on(0);
+                        PF_CUDA(cudaStreamWaitEvent(s0, ev_pass_[g], 0));
+                    }
+                    on(0);
+                    PF_CUDA(cudaStreamEndCapture(s0, &graph_));
+                    PF_CUDA(cudaGraphInstantiate(&gexec_, graph_, 0));
+                } catch (const Error&) {
+                    cudaGraph_t g = nullptr;
+                    cudaStreamEndCapture(s0, &g);
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError();
+                    graph_failed_ = true;
+                    gexec_ = nullptr;
+                }
+            } else {
+                cudaGetLastError();
+                graph_failed_ = true;
+            }
+        }
+        if (gexec_) {
+            on(0);
+            PF_CUDA(cudaGraphLaunch(gexec_, s0));
+        } else {
+            solve();
+        }
+    }
     void sync_all() {
         for (size_t g = 0; g < devs_.size(); g++) {
             on((int)g);
@@ -95,7 +149,6 @@ class MultiPlan {
         const int G = (int)devs_.size();
         halo_bytes_ = gather_bytes_ = 0;
         split_solves_ = 0;
-        gathered_once_ = false;
         for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_begin(); }
         const int nlev = plans_[0]->levels();
         for (int k = nlev - 1; k >= 0; k--) {
@@ -136,55 +189,87 @@ class MultiPlan {
         }
         split_solves_++;
         const int pitch = v[0].args.pitch;
-        // nobody may overwrite a buffer another device is still gathering from (previous solve)
-        if (gathered_once_)
-            for (int g = 0; g < G; g++) {
-                on(g);
-                for (int o = 0; o < G; o++)
-                    if (o != g) PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_gather_[o], 0));
-            }
+        // Every device must have finished all earlier work on its du/dv buffers (previous solve, its
+        // gather, a coarser level solved locally) before a neighbour's first pass starts storing halo
+        // rows into them: one event per device, awaited by all others, opens each split solve.
+        for (int g = 0; g < G; g++) {
+            on(g);
+            PF_CUDA(cudaEventRecord(ev_gather_[g], plans_[g]->stream()));
+        }
+        for (int g = 0; g < G; g++) {
+            on(g);
+            for (int o = 0; o < G; o++)
+                if (o != g) PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_gather_[o], 0));
+        }
         auto band = [&](const Runner::SorPass& ps, int g, int& tb, int& te) {
             tb = (int)((long long)g * ps.ty.ntiles / G);
             te = (int)((long long)(g + 1) * ps.ty.ntiles / G);
         };
+        struct Range { int lo, hi; };
+        auto cut = [](Range a, Range b) { return Range{std::max(a.lo, b.lo), std::min(a.hi, b.hi)}; };
         for (size_t p = 0; p < sched.size(); p++) {
             const Runner::SorPass& ps = sched[p];
+            const bool last = p + 1 == sched.size();
+            // rows each device produces in this pass, rows it must hold before its next step (its next
+            // pass's input rows, or everything after the last pass), and this pass's buffers
+            std::vector<Range> own(G), need(G);
+            std::vector<float*> in_u(G), in_v(G), out_u(G), out_v(G);
+            for (int g = 0; g < G; g++) {
+                int tb, te;
+                band(ps, g, tb, te);
+                own[g] = Range{ps.out_lo(tb), ps.out_hi(te - 1, h)};
+                need[g] = Range{0, h};
+                if (!last) {
+                    band(sched[p + 1], g, tb, te);
+                    need[g] = Range{sched[p + 1].in_lo(tb), sched[p + 1].in_hi(te - 1, h)};
+                }
+                in_u[g] = *v[g].du; in_v[g] = *v[g].dv; out_u[g] = *v[g].du2; out_v[g] = *v[g].dv2;
+            }
+            // launch: halo rows wanted by the ADJACENT bands are pushed by the kernel itself
+            std::vector<Range> pushed_up(G, Range{0, 0}), pushed_dn(G, Range{0, 0});
             for (int g = 0; g < G; g++) {
                 on(g);
                 int tb, te;
                 band(ps, g, tb, te);
-                v[g].runner->launch_pass(v[g].args, ps, *v[g].du, *v[g].dv, *v[g].du2, *v[g].dv2, tb, te);
+                SorPeer<float> peer;
+                if (!last && push_) {
+                    if (g > 0) {
+                        Range r = cut(need[g - 1], own[g]);
+                        if (r.hi > r.lo) { peer.up_du = out_u[g - 1]; peer.up_dv = out_v[g - 1]; peer.up_lo = r.lo; peer.up_hi = r.hi; pushed_up[g] = r; }
+                    }
+                    if (g + 1 < G) {
+                        Range r = cut(need[g + 1], own[g]);
+                        if (r.hi > r.lo) { peer.dn_du = out_u[g + 1]; peer.dn_dv = out_v[g + 1]; peer.dn_lo = r.lo; peer.dn_hi = r.hi; pushed_dn[g] = r; }
+                    }
+                    halo_bytes_ += 2LL * ((peer.up_hi - peer.up_lo) + (peer.dn_hi - peer.dn_lo)) * w * (long long)sizeof(float);
+                }
+                v[g].runner->launch_pass(v[g].args, ps, in_u[g], in_v[g], out_u[g], out_v[g], tb, te, peer);
                 PF_CUDA(cudaEventRecord(ev_pass_[g], plans_[g]->stream()));
-                std::swap(*v[g].du, *v[g].du2);      // the result of this pass is now in du/dv
+            }
+            for (int g = 0; g < G; g++) {          // the result of this pass is now in du/dv
+                std::swap(*v[g].du, *v[g].du2);
                 std::swap(*v[g].dv, *v[g].dv2);
             }
-            const bool last = p + 1 == sched.size();
+            // whatever a device still misses is pulled from its owner; pushes only need the event
             for (int g = 0; g < G; g++) {
                 on(g);
-                // rows device g needs next: everything for the replicated stages after the last pass,
-                // otherwise exactly the rows its next pass reads
-                int need_lo = 0, need_hi = h;
-                if (!last) {
-                    int tb, te;
-                    band(sched[p + 1], g, tb, te);
-                    need_lo = sched[p + 1].in_lo(tb);
-                    need_hi = sched[p + 1].in_hi(te - 1, h);
-                }
+                // a device's next pass stores halo rows into its neighbours' buffers, so it must not
+                // start before they have finished this pass -- even if it needs no rows from them
+                if (g > 0) PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_pass_[g - 1], 0));
+                if (g + 1 < G) PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_pass_[g + 1], 0));
                 for (int o = 0; o < G; o++) {
                     if (o == g) continue;
-                    int tb, te;
-                    band(ps, o, tb, te);
-                    int r0 = std::max(need_lo, ps.out_lo(tb)), r1 = std::min(need_hi, ps.out_hi(te - 1, h));
-                    if (r1 <= r0) continue;
+                    Range r = cut(need[g], own[o]);
+                    if (r.hi <= r.lo) continue;
                     PF_CUDA(cudaStreamWaitEvent(plans_[g]->stream(), ev_pass_[o], 0));
+                    const Range& ps_r = (o == g + 1) ? pushed_up[o] : (o == g - 1 ? pushed_dn[o] : Range{0, 0});
+                    if (ps_r.hi > ps_r.lo && ps_r.lo == r.lo && ps_r.hi == r.hi) continue;   // already delivered by o's kernel
                     long long& ctr = last ? gather_bytes_ : halo_bytes_;
-                    pull_rows(g, *v[g].du, o, *v[o].du, r0, r1, pitch, ctr);
-                    pull_rows(g, *v[g].dv, o, *v[o].dv, r0, r1, pitch, ctr);
+                    pull_rows(g, out_u[g], o, out_u[o], r.lo, r.hi, pitch, ctr);
+                    pull_rows(g, out_v[g], o, out_v[o], r.lo, r.hi, pitch, ctr);
                 }
-                if (last) PF_CUDA(cudaEventRecord(ev_gather_[g], plans_[g]->stream()));
             }
         }
-        gathered_once_ = true;
     }
 
     Params P;
@@ -194,7 +279,11 @@ class MultiPlan {
     std::vector<cudaEvent_t> ev_pass_, ev_gather_;
     long long halo_bytes_ = 0, gather_bytes_ = 0;
     int split_solves_ = 0;
-    bool gathered_once_ = false;
+    cudaGraph_t graph_ = nullptr;
+    cudaGraphExec_t gexec_ = nullptr;
+    cudaEvent_t ev_fork_ = nullptr;
+    bool graph_failed_ = false;
+    bool push_ = true;     // halo rows stored by the producing kernel into the neighbour (PF_MULTI_PULL=1: copy-engine pulls)
 };
 
 }  // namespace pf

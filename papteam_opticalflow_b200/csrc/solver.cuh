@@ -176,7 +176,8 @@ struct SorRunner {
     }
 
     // tile rows [ty_begin, ty_end) of one pass: reads du/dv (if has_input), writes du2/dv2
-    void launch_pass(SorArgs<T> a, const SorPass& ps, T* du, T* dv, T* du2, T* dv2, int ty_begin, int ty_end) {
+    void launch_pass(SorArgs<T> a, const SorPass& ps, T* du, T* dv, T* du2, T* dv2, int ty_begin, int ty_end,
+                     const SorPeer<T>& peer = SorPeer<T>()) {
         const int w = a.w, h = a.h, nrows = ty_end - ty_begin;
         if (nrows <= 0) return;
         a.du_in = ps.has_input ? du : nullptr; a.dv_in = ps.has_input ? dv : nullptr; a.du = du2; a.dv = dv2;
@@ -198,14 +199,14 @@ struct SorRunner {
                 if (packed) {
                     k_sor_rb_tma_pk<kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
                         m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
-                        ps.tx.step, ps.ty.step, ty_begin);
+                        ps.tx.step, ps.ty.step, ty_begin, peer);
                     launched = true;
                 }
             }
             if (!launched)
                 k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
                     m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
-                    ps.tx.step, ps.ty.step, ty_begin);
+                    ps.tx.step, ps.ty.step, ty_begin, peer);
         } else {
             if (ty_begin != 0 || ty_end != ps.ty.ntiles) throw Error(PF_EUNSUPPORTED, "row-band split needs the TMA SOR kernel");
             k_sor_rb_tile<T, kR, kNW><<<dim3(ps.tx.ntiles, ps.ty.ntiles), kNW * 32, 0, st>>>(a, ps.nsw, ps.tx.step, ps.ty.step);

@@ -296,6 +296,16 @@ struct SorMaps {
     CUtensorMap phi, dxy, iu, iv, bu, bv, du, dv;   // du/dv: the INPUT buffers of this pass
 };
 
+// Row-band split over several GPUs: output rows [up_lo, up_hi) are ALSO stored straight into the
+// upper neighbour's output planes and rows [dn_lo, dn_hi) into the lower neighbour's (peer-mapped
+// pointers, posted stores over NVLink), which is the halo the neighbour's next pass reads.  Empty
+// ranges / null pointers on a single GPU.
+template <typename T>
+struct SorPeer {
+    T *up_du = nullptr, *up_dv = nullptr, *dn_du = nullptr, *dn_dv = nullptr;
+    int up_lo = 0, up_hi = 0, dn_lo = 0, dn_hi = 0;
+};
+
 template <typename T, int R, int NW>
 struct SorStage {
     static constexpr int RH = NW * R;
@@ -307,7 +317,7 @@ struct SorStage {
 template <typename T, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
-             T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0) {
+             T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0, SorPeer<T> peer) {
     static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
     typedef typename Vec2<T>::type V2;
     typedef SorStage<T, R, NW> Stage;
@@ -469,6 +479,23 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
                 du_out[o + 1] = du[r][1];
                 dv_out[o + 1] = dv[r][1];
             }
+            // row-band split: the same values go straight into the planes of the neighbour(s) whose next
+            // pass reads this row (a row can be wanted by both neighbours when bands are thin)
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const bool want = side ? (y >= peer.dn_lo && y < peer.dn_hi) : (y >= peer.up_lo && y < peer.up_hi);
+                if (!want) continue;
+                T* pu = side ? peer.dn_du : peer.up_du;
+                T* pv = side ? peer.dn_dv : peer.up_dv;
+                if (v0 && v1) {
+                    *reinterpret_cast<V2*>(pu + o) = V2{du[r][0], du[r][1]};
+                    *reinterpret_cast<V2*>(pv + o) = V2{dv[r][0], dv[r][1]};
+                } else if (v0) {
+                    pu[o] = du[r][0]; pv[o] = dv[r][0];
+                } else if (v1) {
+                    pu[o + 1] = du[r][1]; pv[o + 1] = dv[r][1];
+                }
+            }
         }
     }
 }
@@ -489,7 +516,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out, float* __restrict__ dv_out, int W, int H,
-                int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0) {
+                int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0, SorPeer<float> peer) {
     constexpr int R = 4, RH = NW * R;
     typedef SorStage<float, R, NW> Stage;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -661,6 +688,21 @@ k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out
             } else if (v1) {
                 du_out[o + 1] = u1;
                 dv_out[o + 1] = w1;
+            }
+#pragma unroll
+            for (int side = 0; side < 2; side++) {      // row-band split: see k_sor_rb_tma
+                const bool want = side ? (y >= peer.dn_lo && y < peer.dn_hi) : (y >= peer.up_lo && y < peer.up_hi);
+                if (!want) continue;
+                float* pu = side ? peer.dn_du : peer.up_du;
+                float* pv = side ? peer.dn_dv : peer.up_dv;
+                if (v0 && v1) {
+                    *reinterpret_cast<float2*>(pu + o) = make_float2(u0, u1);
+                    *reinterpret_cast<float2*>(pv + o) = make_float2(w0, w1);
+                } else if (v0) {
+                    pu[o] = u0; pv[o] = w0;
+                } else if (v1) {
+                    pu[o + 1] = u1; pv[o + 1] = w1;
+                }
             }
         }
         // the exchange buffers are reused by the next tile: its first publish(0) must not overtake a
