@@ -113,7 +113,7 @@ struct SorRunner {
     static constexpr int kR = kF64 ? 2 : PF_SOR_R;
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, simple_rb = false, use_tma = true, packed = false;
+    bool lex = false, simple_rb = false, use_tma = true;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148;
     cudaStream_t st = nullptr;
 
@@ -130,13 +130,9 @@ struct SorRunner {
         e = getenv("PF_SOR_TMA");
         use_tma = !(e && !atoi(e));
         PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        e = getenv("PF_SOR_PACKED");
-        packed = !kF64 && !(e && !atoi(e));
         if (!lex && !simple_rb && use_tma) {
             size_t bytes = sor_smem_bytes();
             PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-            if constexpr (!kF64 && kR == 4)
-                PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma_pk<kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         }
         if (lex) {
             int coop = 0, per_sm = 0;
@@ -194,17 +190,7 @@ struct SorRunner {
             m.dv = make_plane_map(ps.has_input ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
             int ntiles = ps.tx.ntiles * nrows;
             size_t smem = sor_smem_bytes();
-            bool launched = false;
-            if constexpr (!kF64 && kR == 4) {
-                if (packed) {
-                    k_sor_rb_tma_pk<kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
-                        m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
-                        ps.tx.step, ps.ty.step, ty_begin, peer);
-                    launched = true;
-                }
-            }
-            if (!launched)
-                k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+            k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
                     m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
                     ps.tx.step, ps.ty.step, ty_begin, peer);
         } else {

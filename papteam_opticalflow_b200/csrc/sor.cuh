@@ -500,217 +500,6 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// FP32 production kernel: k_sor_rb_tma with the half-sweep rewritten for issue rate.
-//   * rows r and r+2 of a thread's 2 x 4 patch always have the same colour, so every per-pixel
-//     quantity is kept as a float2 over that row pair and the whole update runs on Blackwell's
-//     packed FP32 pipe (__ffma2_rn / __fmul2_rn -> SASS FFMA2/FMUL2): 14 packed instructions per two
-//     pixels instead of 28 scalar ones;
-//   * the exchange rows between warps are double buffered by half-sweep parity, so ONE
-//     __syncthreads per half-sweep suffices, and stored as [column parity][lane] (conflict free);
-//   * no per-update selects: the left neighbour outside the region belongs to the discarded halo
-//     (or is TMA zero fill at the image edge); the only exact zero that matters -- the right weight
-//     of image column W-1 when it is the region's last column -- is folded into a weight register.
-// Arithmetic is the same red-black update in the same summation order as k_sor_rb_tma.
-// ------------------------------------------------------------------------------------------------
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-k_sor_rb_tma_pk(const __grid_constant__ SorMaps maps, float* __restrict__ du_out, float* __restrict__ dv_out, int W, int H,
-                int P, float alpha, float omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0, SorPeer<float> peer) {
-    constexpr int R = 4, RH = NW * R;
-    typedef SorStage<float, R, NW> Stage;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
-    __shared__ float ex[2][2][NW][2][2][32];   // [buffer][du|dv][warp][top|bottom][column parity][lane]
-    __shared__ __align__(8) uint64_t full_bar;
-
-    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int HL = 2 * nsw;
-    const int ntiles = ntx * nty;
-    const uint32_t stage_bytes = (uint32_t)(sizeof(float) * (Stage::PHH * Stage::PHW + (has_input ? 7 : 5) * RH * kSorRegionW));
-    const float2 one_m2 = make_float2(1.0f - omega, 1.0f - omega);
-
-    auto issue = [&](int tile) {
-        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
-        const int rx0 = tx * step_x, ry0 = ty * step_y;
-        mbar_expect_tx(&full_bar, stage_bytes);
-        tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
-        tma_load_2d(&st.pl[0][0][0], &maps.dxy, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[1][0][0], &maps.iu, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[2][0][0], &maps.iv, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[3][0][0], &maps.bu, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[4][0][0], &maps.bv, rx0, ry0, &full_bar);
-        if (has_input) {
-            tma_load_2d(&st.pl[5][0][0], &maps.du, rx0, ry0, &full_bar);
-            tma_load_2d(&st.pl[6][0][0], &maps.dv, rx0, ry0, &full_bar);
-        }
-    };
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    int tile = blockIdx.x;
-    if (tid == 0 && tile < ntiles) issue(tile);
-    uint32_t parity = 0;
-
-    for (; tile < ntiles; tile += gridDim.x) {
-        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
-        const int rx0 = tx * step_x, ry0 = ty * step_y;   // multiples of 4
-        const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
-
-        mbar_wait(&full_bar, parity);
-        parity ^= 1;
-
-        // packed state: index [q][p], .x = row q, .y = row q+2 of the patch; p = column parity
-        float2 W2[2][2], NDXY2[2][2], IU2[2][2], IV2[2][2], BU2[2][2], BV2[2][2], DU2[2][2], DV2[2][2];
-        float2 WL2[2], WR2[2];
-        float wu[2];
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int r0 = wp * R + q, r1 = r0 + 2;
-            auto ld = [&](int plane, int row) { return *reinterpret_cast<const float2*>(&st.pl[plane][row][2 * lane]); };
-            const float2 pa = *reinterpret_cast<const float2*>(&st.phi[r0 + 1][2 * lane + 4]);
-            const float2 pb = *reinterpret_cast<const float2*>(&st.phi[r1 + 1][2 * lane + 4]);
-            W2[q][0] = make_float2(pa.x * alpha, pb.x * alpha);
-            W2[q][1] = make_float2(pa.y * alpha, pb.y * alpha);
-            WL2[q] = make_float2(st.phi[r0 + 1][2 * lane + 3] * alpha, st.phi[r1 + 1][2 * lane + 3] * alpha);
-            float2 a = ld(0, r0), b = ld(0, r1);
-            NDXY2[q][0] = make_float2(-a.x, -b.x); NDXY2[q][1] = make_float2(-a.y, -b.y);
-            a = ld(1, r0); b = ld(1, r1); IU2[q][0] = make_float2(a.x, b.x); IU2[q][1] = make_float2(a.y, b.y);
-            a = ld(2, r0); b = ld(2, r1); IV2[q][0] = make_float2(a.x, b.x); IV2[q][1] = make_float2(a.y, b.y);
-            a = ld(3, r0); b = ld(3, r1); BU2[q][0] = make_float2(a.x, b.x); BU2[q][1] = make_float2(a.y, b.y);
-            a = ld(4, r0); b = ld(4, r1); BV2[q][0] = make_float2(a.x, b.x); BV2[q][1] = make_float2(a.y, b.y);
-            if (has_input) {
-                a = ld(5, r0); b = ld(5, r1); DU2[q][0] = make_float2(a.x, b.x); DU2[q][1] = make_float2(a.y, b.y);
-                a = ld(6, r0); b = ld(6, r1); DV2[q][0] = make_float2(a.x, b.x); DV2[q][1] = make_float2(a.y, b.y);
-            } else {
-                DU2[q][0] = DU2[q][1] = DV2[q][0] = DV2[q][1] = make_float2(0.f, 0.f);
-            }
-            // right weight of the odd column: exactly zero when that column is the image's last one and
-            // the region's last one (the neighbour is then neither in the image nor in the region)
-            WR2[q] = (lane == 31 && xa + 1 == W - 1) ? make_float2(0.f, 0.f) : W2[q][1];
-        }
-        {
-            const float2 t = *reinterpret_cast<const float2*>(&st.phi[wp * R][2 * lane + 4]);
-            wu[0] = t.x * alpha; wu[1] = t.y * alpha;
-        }
-        auto publish = [&](int buf) {
-            ex[buf][0][wp][0][0][lane] = DU2[0][0].x; ex[buf][0][wp][0][1][lane] = DU2[0][1].x;   // top row (r=0)
-            ex[buf][1][wp][0][0][lane] = DV2[0][0].x; ex[buf][1][wp][0][1][lane] = DV2[0][1].x;
-            ex[buf][0][wp][1][0][lane] = DU2[1][0].y; ex[buf][0][wp][1][1][lane] = DU2[1][1].y;   // bottom row (r=3)
-            ex[buf][1][wp][1][0][lane] = DV2[1][0].y; ex[buf][1][wp][1][1][lane] = DV2[1][1].y;
-        };
-        publish(0);
-        __syncthreads();   // stage consumed by everyone, exchange rows published
-        {
-            const int next = tile + gridDim.x;
-            if (tid == 0 && next < ntiles) issue(next);   // overlaps the sweeps below
-        }
-
-        int buf = 0;
-        for (int s = 0; s < nsw; s++) {
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                // row 0 is updated in column p = c, row 3 in column p = (3 + c) & 1 = 1 - c
-                float up_du = 0.f, up_dv = 0.f, dn_du = 0.f, dn_dv = 0.f;
-                if (wp > 0) {
-                    up_du = ex[buf][0][wp - 1][1][c][lane];
-                    up_dv = ex[buf][1][wp - 1][1][c][lane];
-                }
-                if (wp < NW - 1) {
-                    dn_du = ex[buf][0][wp + 1][0][1 - c][lane];
-                    dn_dv = ex[buf][1][wp + 1][0][1 - c][lane];
-                }
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int p = (q + c) & 1;
-                    float2 LW, LDU, LDV, RW, RDU, RDV;
-                    if (p == 1) {
-                        LW = W2[q][0]; LDU = DU2[q][0]; LDV = DV2[q][0];
-                        RW = WR2[q];
-                        RDU.x = __shfl_down_sync(0xffffffffu, DU2[q][0].x, 1); RDU.y = __shfl_down_sync(0xffffffffu, DU2[q][0].y, 1);
-                        RDV.x = __shfl_down_sync(0xffffffffu, DV2[q][0].x, 1); RDV.y = __shfl_down_sync(0xffffffffu, DV2[q][0].y, 1);
-                    } else {
-                        LW = WL2[q];
-                        LDU.x = __shfl_up_sync(0xffffffffu, DU2[q][1].x, 1); LDU.y = __shfl_up_sync(0xffffffffu, DU2[q][1].y, 1);
-                        LDV.x = __shfl_up_sync(0xffffffffu, DV2[q][1].x, 1); LDV.y = __shfl_up_sync(0xffffffffu, DV2[q][1].y, 1);
-                        RW = W2[q][0]; RDU = DU2[q][1]; RDV = DV2[q][1];
-                    }
-                    float2 UW, UDU, UDV, DDU, DDV;
-                    if (q == 0) {   // rows (0, 2): up = (external, row 1), down = rows (1, 3)
-                        UW = make_float2(wu[p], W2[1][p].x);
-                        UDU = make_float2(up_du, DU2[1][p].x);
-                        UDV = make_float2(up_dv, DV2[1][p].x);
-                        DDU = DU2[1][p]; DDV = DV2[1][p];
-                    } else {        // rows (1, 3): up = rows (0, 2), down = (row 2, external)
-                        UW = W2[0][p]; UDU = DU2[0][p]; UDV = DV2[0][p];
-                        DDU = make_float2(DU2[0][p].y, dn_du);
-                        DDV = make_float2(DV2[0][p].y, dn_dv);
-                    }
-                    const float2 CW = W2[q][p];
-                    float2 a1 = BU2[q][p], a2 = BV2[q][p];
-                    a1 = __ffma2_rn(LW, LDU, a1); a2 = __ffma2_rn(LW, LDV, a2);
-                    a1 = __ffma2_rn(RW, RDU, a1); a2 = __ffma2_rn(RW, RDV, a2);
-                    a1 = __ffma2_rn(UW, UDU, a1); a2 = __ffma2_rn(UW, UDV, a2);
-                    a1 = __ffma2_rn(CW, DDU, a1); a2 = __ffma2_rn(CW, DDV, a2);
-                    a1 = __ffma2_rn(NDXY2[q][p], DV2[q][p], a1);
-                    const float2 nu = __ffma2_rn(IU2[q][p], a1, __fmul2_rn(one_m2, DU2[q][p]));
-                    a2 = __ffma2_rn(NDXY2[q][p], nu, a2);
-                    const float2 nv = __ffma2_rn(IV2[q][p], a2, __fmul2_rn(one_m2, DV2[q][p]));
-                    DU2[q][p] = nu;
-                    DV2[q][p] = nv;
-                }
-                buf ^= 1;
-                publish(buf);
-                __syncthreads();
-            }
-        }
-
-        const int ox_lo = tx > 0 ? rx0 + HL : 0;
-        const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
-        const int oy_lo = ty > 0 ? ry0 + HL : 0;
-        const int oy_hi = (ry0 + RH >= H) ? H : ry0 + RH - HL;
-        const bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int y = ya + r, q = r & 1;
-            if (y < oy_lo || y >= oy_hi) continue;
-            const float u0 = (r & 2) ? DU2[q][0].y : DU2[q][0].x, u1 = (r & 2) ? DU2[q][1].y : DU2[q][1].x;
-            const float w0 = (r & 2) ? DV2[q][0].y : DV2[q][0].x, w1 = (r & 2) ? DV2[q][1].y : DV2[q][1].x;
-            const size_t o = (size_t)y * P + xa;
-            if (v0 && v1) {
-                *reinterpret_cast<float2*>(du_out + o) = make_float2(u0, u1);
-                *reinterpret_cast<float2*>(dv_out + o) = make_float2(w0, w1);
-            } else if (v0) {
-                du_out[o] = u0;
-                dv_out[o] = w0;
-            } else if (v1) {
-                du_out[o + 1] = u1;
-                dv_out[o + 1] = w1;
-            }
-#pragma unroll
-            for (int side = 0; side < 2; side++) {      // row-band split: see k_sor_rb_tma
-                const bool want = side ? (y >= peer.dn_lo && y < peer.dn_hi) : (y >= peer.up_lo && y < peer.up_hi);
-                if (!want) continue;
-                float* pu = side ? peer.dn_du : peer.up_du;
-                float* pv = side ? peer.dn_dv : peer.up_dv;
-                if (v0 && v1) {
-                    *reinterpret_cast<float2*>(pu + o) = make_float2(u0, u1);
-                    *reinterpret_cast<float2*>(pv + o) = make_float2(w0, w1);
-                } else if (v0) {
-                    pu[o] = u0; pv[o] = w0;
-                } else if (v1) {
-                    pu[o + 1] = u1; pv[o + 1] = w1;
-                }
-            }
-        }
-        // the exchange buffers are reused by the next tile: its first publish(0) must not overtake a
-        // warp still reading buffer 0 in this tile's last half-sweep -- that read happened before the
-        // final barrier above (buffer index is back to 0 after an even number of half-sweeps)
-    }
-}
-
 // Tiling of an image dimension of size n by regions of size `region` whose exact window shrinks by
 // `halo` on every side that is not an image edge.  Region origins are step*k.
 struct SorTiling {
