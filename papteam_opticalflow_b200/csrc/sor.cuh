@@ -479,21 +479,31 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
                 du_out[o + 1] = du[r][1];
                 dv_out[o + 1] = dv[r][1];
             }
-            // row-band split: the same values go straight into the planes of the neighbour(s) whose next
-            // pass reads this row (a row can be wanted by both neighbours when bands are thin)
+        }
+        // row-band split over several GPUs (kernel-uniform branch, not taken on a single GPU): the same
+        // values go straight into the planes of the neighbour(s) whose next pass reads the row; a row can
+        // be wanted by both neighbours when bands are thin
+        if (peer.up_hi > peer.up_lo || peer.dn_hi > peer.dn_lo) {
 #pragma unroll
-            for (int side = 0; side < 2; side++) {
-                const bool want = side ? (y >= peer.dn_lo && y < peer.dn_hi) : (y >= peer.up_lo && y < peer.up_hi);
-                if (!want) continue;
-                T* pu = side ? peer.dn_du : peer.up_du;
-                T* pv = side ? peer.dn_dv : peer.up_dv;
-                if (v0 && v1) {
-                    *reinterpret_cast<V2*>(pu + o) = V2{du[r][0], du[r][1]};
-                    *reinterpret_cast<V2*>(pv + o) = V2{dv[r][0], dv[r][1]};
-                } else if (v0) {
-                    pu[o] = du[r][0]; pv[o] = dv[r][0];
-                } else if (v1) {
-                    pu[o + 1] = du[r][1]; pv[o + 1] = dv[r][1];
+            for (int r = 0; r < R; r++) {
+                const int y = ya + r;
+                if (y < oy_lo || y >= oy_hi) continue;
+                const bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
+                const size_t o = (size_t)y * P + xa;
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const bool want = side ? (y >= peer.dn_lo && y < peer.dn_hi) : (y >= peer.up_lo && y < peer.up_hi);
+                    if (!want) continue;
+                    T* pu = side ? peer.dn_du : peer.up_du;
+                    T* pv = side ? peer.dn_dv : peer.up_dv;
+                    if (v0 && v1) {
+                        *reinterpret_cast<V2*>(pu + o) = V2{du[r][0], du[r][1]};
+                        *reinterpret_cast<V2*>(pv + o) = V2{dv[r][0], dv[r][1]};
+                    } else if (v0) {
+                        pu[o] = du[r][0]; pv[o] = dv[r][0];
+                    } else if (v1) {
+                        pu[o + 1] = du[r][1]; pv[o + 1] = dv[r][1];
+                    }
                 }
             }
         }
