@@ -218,7 +218,7 @@ def run_ours(args):
     #      through ONE pf_batch_flow call so that the copy legs of some pairs overlap the solves of
     #      others instead of every step starting with B simultaneous uploads. ----
     os.environ.setdefault("PF_BATCH_STREAMS", str(min(B, 8)))
-    ring = 3 * B                                        # output slots, reused cyclically
+    ring = B + 8                                        # output slots, reused cyclically (more than the workers in flight)
     host_outs = [tuple(pinned_like(lib, np.zeros(s))[0] for s in ((H, W), (H, W), (H, W, CH))) for _ in range(ring)]
     def e2e_run(nsteps):
         n = nsteps * B

@@ -114,7 +114,7 @@ struct SorRunner {
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
     bool lex = false, simple_rb = false, use_tma = true;
-    int forced_fuse = 0, coop_max_blocks = 1, sms = 148;
+    int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     cudaStream_t st = nullptr;
 
     // stage + double-buffered exchange rows + alignment slack
@@ -133,6 +133,9 @@ struct SorRunner {
         if (!lex && !simple_rb && use_tma) {
             size_t bytes = sor_smem_bytes();
             PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            int per_sm = 1;
+            PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_rb_tma<T, kR, kNW>, kNW * 32, bytes));
+            ctas_per_sm = std::max(1, per_sm);
         }
         if (lex) {
             int coop = 0, per_sm = 0;
@@ -190,7 +193,7 @@ struct SorRunner {
             m.dv = make_plane_map(ps.has_input ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
             int ntiles = ps.tx.ntiles * nrows;
             size_t smem = sor_smem_bytes();
-            k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32, smem, st>>>(
+            k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms * ctas_per_sm), kNW * 32, smem, st>>>(
                     m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
                     ps.tx.step, ps.ty.step, ty_begin, peer);
         } else {

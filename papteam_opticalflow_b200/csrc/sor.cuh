@@ -314,8 +314,11 @@ struct SorStage {
     alignas(128) T pl[7][RH][kSorRegionW];   // dxy, iu, iv, bu, bv, du, dv (each plane a multiple of 128 B)
 };
 
+#ifndef PF_SOR_MINB
+#define PF_SOR_MINB 1
+#endif
 template <typename T, int R, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, PF_SOR_MINB)
 k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
              T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0, SorPeer<T> peer) {
     static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
