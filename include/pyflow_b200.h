@@ -125,6 +125,18 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                   int nSORIterations, int colType, int h, int w, int c, int mode,
                   const int* devices, int ndevices, double* seconds);
 
+/* ---- sequences (SURVEY.md 8f "next" rows f1 + f2): nframes uint8 HWC frames (as PIL decodes
+ * them, Par/OpticalFlowCalculation.py:66-67) -> nframes-1 flows of the consecutive pairs (t, t+1)
+ * (pairing rule Par/InputCreation/TestImagePairGenerator.py:151-171) as interleaved float32 (u, v).
+ * The /255 conversion runs on the device in double (bit-identical pixel values), every frame's
+ * pyramid is built once and reused as the next pair's first image, and only uint8 in / float32
+ * out cross PCIe.  Flows equal the pairwise entry points' (u, v) cast to float32.  Contiguous
+ * chunks of the sequence are spread over devices x PF_BATCH_STREAMS workers; no collective. */
+int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* const* flows,
+                        double alpha, double ratio, int minWidth, int levels, int nOuterFPIterations,
+                        int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,
+                        int mode, const int* devices, int ndevices, double* seconds);
+
 /* ---- ONE large pair over several GPUs (BASELINE config 5): every device runs the
  * cheap stages redundantly, the SOR solve is split into row bands with peer-to-peer halo exchange
  * over NVLink after every fused-sweep pass (cudaMemcpyPeerAsync ordered by events, no collective).

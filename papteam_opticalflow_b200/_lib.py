@@ -56,6 +56,8 @@ def lib():
         "pf_plan_level_timings": (i, [v, dp, i]),
         "pf_multi_solve": (i, [C.POINTER(v), i, i, dp]),
         "pf_batch_flow": (i, [i, dpp, dpp, dpp, dpp, dpp, d, d, i, i, i, i, i, i, i, i, i, i, ip, i, dp]),
+        "pf_sequence_flow_u8": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_float)), d, d, i, i, i, i, i, i, i, i, i, i,
+                                    ip, i, dp]),
         "pf_multigpu_flow": (i, [dp, dp, dp, dp, dp, d, d, i, i, i, i, i, i, i, i, i, ip, i, C.c_longlong, dp]),
         "pf_stage_pyramid": (i, [dp, dp, i, i, i, d, i, i, i]),
         "pf_stage_im2feature": (i, [dp, dp, i, i, i, i, i, i]),

@@ -396,6 +396,52 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     return PF_OK;
 }
 
+int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* const* flows, double alpha, double ratio,
+                        int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
+                        const int* devices, int ndevices, double* seconds) {
+    if (nframes < 0 || ndevices < 1 || !devices) return fail(PF_EINVAL, "bad sequence arguments");
+    const int npairs = nframes > 0 ? nframes - 1 : 0;
+    if (npairs > 0 && (!frames || !flows)) return fail(PF_EINVAL, "NULL argument");
+    int r;
+    if ((r = check_image(h, w, c)) || (r = check_mode(mode))) return r;
+    for (int d = 0; d < ndevices; d++)
+        if ((r = check_device(devices[d]))) return r;
+    auto t0 = std::chrono::steady_clock::now();
+    // contiguous chunks of the pair list per worker, so that inside a chunk every frame's pyramid is
+    // built once and reused as the next pair's first image
+    const char* env = getenv("PF_BATCH_STREAMS");
+    int per_dev = env ? atoi(env) : 4;
+    if (per_dev < 1 || mode_is_lex(mode)) per_dev = 1;
+    const int nworkers = std::max(1, std::min(npairs, ndevices * per_dev));
+    std::vector<std::thread> workers;
+    std::vector<int> status((size_t)nworkers, PF_OK);
+    std::vector<std::string> messages((size_t)nworkers);
+    for (int wk = 0; wk < nworkers && npairs > 0; wk++) {
+        workers.emplace_back([&, wk]() {
+            const int p0 = (int)((long long)wk * npairs / nworkers), p1 = (int)((long long)(wk + 1) * npairs / nworkers);
+            if (p1 <= p0) return;
+            int rc = PF_OK;
+            Params pp{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[wk % ndevices]};
+            pf_plan* pl = pool_acquire(pp, rc);
+            if (rc == PF_OK) {
+                rc = guarded([&]() -> int {
+                    pl->impl->seq_first(frames[p0]);
+                    for (int p = p0; p < p1; p++) pl->impl->seq_next(frames[p + 1], flows[p]);
+                    return PF_OK;
+                });
+            }
+            if (rc) messages[(size_t)wk] = g_err;
+            if (pl) pool_release(pl);
+            status[(size_t)wk] = rc;
+        });
+    }
+    for (auto& t : workers) t.join();
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int wk = 0; wk < nworkers; wk++)
+        if (status[(size_t)wk]) return fail(status[(size_t)wk], messages[(size_t)wk]);
+    return PF_OK;
+}
+
 int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2, double alpha,
                      double ratio, int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w,
                      int c, const int* devices, int ndevices, long long split_min_pixels, double* stats) {

@@ -29,6 +29,25 @@ __global__ void k_export_hwc(Img<T> src, double* __restrict__ dst) {
     for (int k = 0; k < src.c; k++) d[k] = (double)src.ch(k)[(size_t)y * src.pitch + x];
 }
 
+// Compact boundary for sequences ("next" rows f1/f2 of SURVEY.md 8f): uint8 HWC frames in -- the
+// conversion the reference driver does on the host, astype(float)/255. (Par/OpticalFlowCalculation.py:
+// 70-71), evaluated in double so the pixel values are bit-identical -- and the flow out as
+// interleaved float32 (u, v), the driver's `flow = concat(u, v)` (:76).
+template <typename T>
+__global__ void k_import_u8(const unsigned char* __restrict__ src, Img<T> dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dst.w) return;
+    const unsigned char* s = src + ((size_t)y * dst.w + x) * dst.c;
+    for (int k = 0; k < dst.c; k++) dst.ch(k)[(size_t)y * dst.pitch + x] = (T)((double)s[k] / 255.0);
+}
+
+template <typename T>
+__global__ void k_export_flow_f32(const T* __restrict__ u, const T* __restrict__ v, int pitch, int w, float2* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    out[(size_t)y * w + x] = make_float2((float)u[(size_t)y * pitch + x], (float)v[(size_t)y * pitch + x]);
+}
+
 template <typename T>
 __global__ void k_fill(Img<T> img, T value) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;

@@ -28,6 +28,8 @@ struct PlanBase {
     virtual void profile(double* timings, double* counters) = 0;
     virtual int level_timings(double* out, int max_levels) const = 0;
     virtual void solve_async(int repeats) = 0;   // enqueue only
+    virtual void seq_first(const unsigned char* frame) = 0;
+    virtual void seq_next(const unsigned char* frame, float* flow) = 0;
     virtual cudaStream_t stream() const = 0;
     virtual int device() const = 0;
 };
@@ -272,6 +274,7 @@ class Plan : public PlanBase {
     ~Plan() override {
         cudaSetDevice(P.device);
         if (gexec_) cudaGraphExecDestroy(gexec_);
+        for (auto& g : gexec_seq_) if (g) cudaGraphExecDestroy(g);
         if (graph_) cudaGraphDestroy(graph_);
         for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
         for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
@@ -538,8 +541,8 @@ class Plan : public PlanBase {
     int level_w(int k) const { return geo_[k].w; }
     int level_h(int k) const { return geo_[k].h; }
 
-    // -- Construction: import + both pyramids (S/GaussianPyramid.cpp:79-108) --
-    void ph_begin() {
+    // filter taps, eps, pointer roles on entry
+    void ph_ctx() {
         const double d5raw[5] = {1.0 / 12, -8.0 / 12, 0.0 / 12, 8.0 / 12, -1.0 / 12};
         const double g5raw[5] = {0.02, 0.11, 0.74, 0.11, 0.02};
         const double d3raw[3] = {-0.5, 0, 0.5};
@@ -549,30 +552,43 @@ class Plan : public PlanBase {
         c.du_e = du_; c.dv_e = dv_; c.du2_e = du2_; c.dv2_e = dv2_;
         c.u_e = u_; c.v_e = v_; c.u2_e = u2_; c.v2_e = v2_;
         c.pw = c.ph = 0;
-        set_phase(PF_T_CONSTRUCTION, 0);
-        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in1_, pyr1_[0]);
-        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in2_, pyr2_[0]);
-        launches_ += 2;
-        for (int side = 0; side < 2; side++) {
-            auto& pyr = side ? pyr2_ : pyr1_;
-            for (int i = 1; i < nlev_; i++) {
-                const Level& g = geo_[i];
-                const Img<T>& src = pyr[g.src];
-                Img<T> blurred = src;
-                if (g.half > 0) {   // half-width 0 is the identity filter (level 1, quirk Q2)
-                    Taps<T> gt = make_taps<T>(g.taps.data(), g.half);
-                    blurred = view(b_out_, src.w, src.h, src.c);
-                    filter_hv(src, blurred, gt, gt);
-                }
-                k_resize<T><<<grid2(g.w, g.h), 128, 0, st_>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
-                launches_++;
+    }
+
+    // Gaussian pyramid of one frame from its level 0 (S/GaussianPyramid.cpp:79-108)
+    void ph_pyramid(int side) {
+        auto& pyr = side ? pyr2_ : pyr1_;
+        for (int i = 1; i < nlev_; i++) {
+            const Level& g = geo_[i];
+            const Img<T>& src = pyr[g.src];
+            Img<T> blurred = src;
+            if (g.half > 0) {   // half-width 0 is the identity filter (level 1, quirk Q2)
+                Taps<T> gt = make_taps<T>(g.taps.data(), g.half);
+                blurred = view(b_out_, src.w, src.h, src.c);
+                filter_hv(src, blurred, gt, gt);
             }
+            k_resize<T><<<grid2(g.w, g.h), 128, 0, st_>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
+            launches_++;
         }
+    }
+
+    void ph_lap_init() {
         if (kF64 && lex_) {
             double lap0[64];
             for (int i = 0; i < 64; i++) lap0[i] = 0.02;   // S/OpticalFlow.cpp:773-775
             PF_CUDA(cudaMemcpyAsync(d_lap_, lap0, sizeof(lap0), cudaMemcpyHostToDevice, st_));
         }
+    }
+
+    // -- Construction: import + both pyramids --
+    void ph_begin() {
+        ph_ctx();
+        set_phase(PF_T_CONSTRUCTION, 0);
+        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in1_, pyr1_[0]);
+        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in2_, pyr2_[0]);
+        launches_ += 2;
+        ph_pyramid(0);
+        ph_pyramid(1);
+        ph_lap_init();
     }
 
     // -- Allocation: features, flow upsampling, warp (S/OpticalFlow.cpp:790-818); smoothed Im1 --
@@ -714,11 +730,87 @@ class Plan : public PlanBase {
         k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
         k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(vo, d_vy_);
         launches_ += 3;
+        ph_restore();
+    }
+
+    // restore the pointer roles so that a captured graph and a later eager run agree
+    void ph_restore() {
+        Ctx& c = cx_;
         PF_CHECK_LAUNCH();
-        // restore the pointer roles so that a captured graph and a later eager run agree
         du_ = c.du_e; dv_ = c.dv_e; du2_ = c.du2_e; dv2_ = c.dv2_e;
         u_ = c.u_e; v_ = c.v_e; u2_ = c.u2_e; v2_ = c.v2_e;
     }
+
+    void ph_levels() {
+        for (int k = nlev_ - 1; k >= 0; k--) {
+            ph_level(k);
+            for (int it = 0; it < n_outer_at(k); it++) {
+                ph_getdxs(k);
+                for (int hh = 0; hh < P.n_inner; hh++) {
+                    ph_assemble(k, hh);
+                    ph_sor(k);
+                }
+                ph_update(k);
+            }
+        }
+    }
+
+    // ---- sequence mode: consecutive pairs share a frame, so the pyramid
+    //      of frame t+1 built for pair t is pair t+1's "Im1" pyramid; frames arrive as uint8, the flow
+    //      leaves as interleaved float32.  Same arithmetic as the pairwise path (bit-identical flow).
+    void seq_first(const unsigned char* frame) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        size_t n = (size_t)P.h * P.w * P.c;
+        PF_CUDA(cudaMemcpyAsync(d_in1_, frame, n, cudaMemcpyHostToDevice, st_));
+        k_import_u8<T><<<grid2(P.w, P.h), 128, 0, st_>>>(reinterpret_cast<const unsigned char*>(d_in1_), pyr2_[0]);
+        ph_pyramid(1);
+        PF_CHECK_LAUNCH();
+    }
+
+    void seq_next(const unsigned char* frame, float* flow) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        std::swap(pyr1_, pyr2_);            // the newer frame of the previous pair becomes Im1
+        seq_parity_ ^= 1;
+        size_t n = (size_t)P.h * P.w * P.c;
+        PF_CUDA(cudaMemcpyAsync(d_in1_, frame, n, cudaMemcpyHostToDevice, st_));
+        if (use_graph_) {
+            cudaGraphExec_t& ge = gexec_seq_[seq_parity_];
+            if (!ge) {
+                cudaGraph_t g = nullptr;
+                PF_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+                try {
+                    enqueue_seq_pair();
+                } catch (...) {
+                    cudaStreamEndCapture(st_, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                PF_CUDA(cudaStreamEndCapture(st_, &g));
+                PF_CUDA(cudaGraphInstantiate(&ge, g, 0));
+                cudaGraphDestroy(g);
+            }
+            PF_CUDA(cudaGraphLaunch(ge, st_));
+        } else {
+            enqueue_seq_pair();
+        }
+        PF_CUDA(cudaMemcpyAsync(flow, d_vx_, (size_t)P.h * P.w * sizeof(float2), cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaStreamSynchronize(st_));
+    }
+
+  private:
+    void enqueue_seq_pair() {
+        ph_ctx();
+        k_import_u8<T><<<grid2(P.w, P.h), 128, 0, st_>>>(reinterpret_cast<const unsigned char*>(d_in1_), pyr2_[0]);
+        launches_++;
+        ph_pyramid(1);
+        ph_lap_init();
+        ph_levels();
+        k_export_flow_f32<T><<<grid2(P.w, P.h), 128, 0, st_>>>(u_, v_, pitch_for(P.w), P.w, reinterpret_cast<float2*>(d_vx_));
+        launches_++;
+        ph_restore();
+    }
+
+  public:
 
     // buffers the cooperative (row-band) SOR of MultiPlan works on
     struct SorView {
@@ -740,17 +832,7 @@ class Plan : public PlanBase {
   private:
     void enqueue_solve() {
         ph_begin();
-        for (int k = nlev_ - 1; k >= 0; k--) {
-            ph_level(k);
-            for (int it = 0; it < n_outer_at(k); it++) {
-                ph_getdxs(k);
-                for (int hh = 0; hh < P.n_inner; hh++) {
-                    ph_assemble(k, hh);
-                    ph_sor(k);
-                }
-                ph_update(k);
-            }
-        }
+        ph_levels();
         ph_end();
     }
 
@@ -772,6 +854,8 @@ class Plan : public PlanBase {
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t gexec_ = nullptr;
+    cudaGraphExec_t gexec_seq_[2] = {nullptr, nullptr};
+    int seq_parity_ = 0;
     std::vector<Span> spans_;
     std::vector<double> level_ms_;
     size_t span_used_ = 0;

@@ -212,6 +212,37 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
     return vx, vy, wi
 
 
+def sequence_flow(frames, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7, nInnerFPIterations=1,
+                  nSORIterations=30, colType=0, levels=0, mode=None, devices=None):
+    """Flows of the consecutive pairs of a frame sequence.
+
+    frames: list of (h, w, c) uint8 C-contiguous arrays (what PIL decodes; the reference driver converts
+    them with astype(float)/255. before calling pyflow -- here that happens on the device).
+    Returns ([flow_0, ..., flow_{n-2}], seconds) with flow_t an (h, w, 2) float32 array (u, v) of pair
+    (t, t+1), equal to coarse2fine_flow(frames[t]/255., frames[t+1]/255., ...) cast to float32."""
+    L = _lib.lib()
+    n = len(frames)
+    if n < 2:
+        return [], 0.0
+    for f in frames:
+        if not isinstance(f, np.ndarray) or f.dtype != np.uint8 or f.ndim != 3 or not f.flags["C_CONTIGUOUS"]:
+            raise ValueError("frames must be C-contiguous (h, w, c) uint8 arrays")
+        if f.shape != frames[0].shape:
+            raise ValueError("all frames of a sequence must share one shape")
+    if devices is None:
+        devices = list(range(max(1, L.pf_device_count())))
+    h, w, c = frames[0].shape
+    flows = [np.zeros((h, w, 2), dtype=np.float32) for _ in range(n - 1)]
+    fp = (C.POINTER(C.c_ubyte) * n)(*[f.ctypes.data_as(C.POINTER(C.c_ubyte)) for f in frames])
+    op = (C.POINTER(C.c_float) * (n - 1))(*[f.ctypes.data_as(C.POINTER(C.c_float)) for f in flows])
+    dev = (C.c_int * len(devices))(*devices)
+    secs = C.c_double()
+    check(L.pf_sequence_flow_u8(n, fp, op, float(alpha), float(ratio), int(minWidth), int(levels), int(nOuterFPIterations),
+                                int(nInnerFPIterations), int(nSORIterations), int(colType), h, w, c, _mode_id(mode), dev,
+                                len(devices), C.byref(secs)))
+    return flows, secs.value
+
+
 def coarse2fine_flow_multigpu(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,
                               nInnerFPIterations=1, nSORIterations=30, colType=0, levels=0, devices=None,
                               split_min_pixels=-1):

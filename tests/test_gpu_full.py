@@ -316,3 +316,46 @@ def test_row_band_split_on_real_peers_if_present():
     u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=list(range(min(n, 4))), split_min_pixels=50000)
     assert st["split_solves"] > 0
     assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+
+
+def _u8_frame(width, idx):
+    from PIL import Image
+    import os
+    from conftest import GOLDEN
+    return np.ascontiguousarray(np.array(Image.open(os.path.join(GOLDEN, "frames", "hcm%d_%05d.jpg" % (width, idx)))))
+
+
+@pytest.mark.parametrize("mode", ["fp32_redblack", "fp64_wavefront"])
+def test_sequence_mode_equals_pairwise_calls(mode, monkeypatch):
+    """uint8 frames in, float32 flows out, each frame's pyramid built once.
+    The result must be the pairwise entry point's flow (same arithmetic) rounded to float32 --
+    for any chunking of the sequence over workers."""
+    idx = [1, 2, 30, 31, 1, 30]
+    frames = [_u8_frame(240, i) for i in idx]
+    want = []
+    for a, b in zip(frames[:-1], frames[1:]):
+        u, v, _ = pyflow.coarse2fine_flow(a.astype(float) / 255., b.astype(float) / 255., 0.012, 0.75, 20, 7, 1, 30, 0, mode=mode)
+        want.append(np.stack([u, v], axis=-1).astype(np.float32))
+    for streams in ("1", "2", "4"):
+        monkeypatch.setenv("PF_BATCH_STREAMS", streams)
+        flows, secs = pyflow.sequence_flow(frames, mode=mode, devices=[0])
+        assert len(flows) == len(frames) - 1 and secs > 0
+        for f, g in zip(flows, want):
+            assert f.dtype == np.float32 and f.shape == g.shape
+            assert np.array_equal(f, g), np.abs(f - g).max()
+    # a second sequence through the pooled plans (other parity of the ping-pong pyramids)
+    flows2, _ = pyflow.sequence_flow(frames[1:4], mode=mode, devices=[0])
+    assert np.array_equal(flows2[0], want[1]) and np.array_equal(flows2[1], want[2])
+    # the pair entry point still works on the same pooled plan after pyramid swaps
+    u, v, _ = pyflow.coarse2fine_flow(frames[0].astype(float) / 255., frames[1].astype(float) / 255., 0.012, 0.75, 20, 7, 1, 30, 0, mode=mode)
+    assert np.array_equal(np.stack([u, v], axis=-1).astype(np.float32), want[0])
+
+
+def test_sequence_mode_argument_errors():
+    assert pyflow.sequence_flow([]) == ([], 0.0)
+    f = _u8_frame(240, 1)
+    assert pyflow.sequence_flow([f]) == ([], 0.0)
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f.astype(float)])
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f[:-1]])
