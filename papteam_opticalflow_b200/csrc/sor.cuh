@@ -458,7 +458,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
                 }
                 buf ^= 1;
                 publish(buf);      // readers of the other buffer are at most one barrier behind
-                __syncthreads();
+                __syncthreads();   // (pairwise 64-thread named barriers between neighbouring warps measured 18 % slower)
             }
         }
 
@@ -466,21 +466,35 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
         const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
         const int oy_lo = ty > 0 ? ry0 + HL : 0;
         const int oy_hi = (ry0 + RH >= H) ? H : ry0 + RH - HL;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            int y = ya + r;
-            if (y < oy_lo || y >= oy_hi) continue;
-            bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
-            size_t o = (size_t)y * P + xa;
+        // write back the window that is still exact.  Column validity does not depend on the row and the
+        // valid rows of a warp are one interval, so the common case is R predicated 8-byte store pairs
+        // off two running pointers (a column pair is split only in the last column of an odd-width level).
+        {
+            const bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
+            const int r_lo = oy_lo - ya;
+            const unsigned r_n = (unsigned)max(oy_hi - oy_lo, 0);
+            char* const pu = reinterpret_cast<char*>(du_out) + ((size_t)ya * P + xa) * sizeof(T);
+            const ptrdiff_t to_dv = reinterpret_cast<char*>(dv_out) - reinterpret_cast<char*>(du_out);
+            const unsigned pitch_b = (unsigned)P * (unsigned)sizeof(T);
             if (v0 && v1) {
-                *reinterpret_cast<V2*>(du_out + o) = V2{du[r][0], du[r][1]};
-                *reinterpret_cast<V2*>(dv_out + o) = V2{dv[r][0], dv[r][1]};
-            } else if (v0) {
-                du_out[o] = du[r][0];
-                dv_out[o] = dv[r][0];
-            } else if (v1) {
-                du_out[o + 1] = du[r][1];
-                dv_out[o + 1] = dv[r][1];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    char* q = pu + (size_t)((unsigned)r * pitch_b);
+                    if ((unsigned)(r - r_lo) < r_n) {
+                        *reinterpret_cast<V2*>(q) = V2{du[r][0], du[r][1]};
+                        *reinterpret_cast<V2*>(q + to_dv) = V2{dv[r][0], dv[r][1]};
+                    }
+                }
+            } else if (v0 || v1) {
+                const int k = v1 ? 1 : 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    T* q = reinterpret_cast<T*>(pu + (size_t)((unsigned)r * pitch_b)) + k;
+                    if ((unsigned)(r - r_lo) < r_n) {
+                        *q = v1 ? du[r][1] : du[r][0];
+                        *reinterpret_cast<T*>(reinterpret_cast<char*>(q) + to_dv) = v1 ? dv[r][1] : dv[r][0];
+                    }
+                }
             }
         }
         // row-band split over several GPUs (kernel-uniform branch, not taken on a single GPU): the same
