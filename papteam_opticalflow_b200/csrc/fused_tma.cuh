@@ -17,11 +17,13 @@
 #pragma once
 #include "kernels.cuh"
 #include "tma.cuh"
+#include <type_traits>
 
 namespace pf {
 
 struct FusedMaps {
     CUtensorMap wf, s1;   // (W, H, C) planar tensors: warped Im2 features, smoothed Im1 features
+    CUtensorMap u, v;     // (W, H) flow planes, box 72 x (TY+2)
 };
 
 template <typename T, int TY>
@@ -34,8 +36,11 @@ struct FusedSmem {
     T dt[TY][TX];
 };
 
+#ifndef PF_FUSED_MINB
+#define PF_FUSED_MINB 4   // 4 CTAs per SM (<= 64 registers, 32 B of spill) measured 13 % faster than 3 CTAs at 80 registers
+#endif
 template <typename T, int TY, int SEG>
-__global__ void __launch_bounds__(64 * SEG)
+__global__ void __launch_bounds__(64 * SEG, sizeof(T) == 4 ? PF_FUSED_MINB : 1)
 k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     typedef FusedSmem<T, TY> Smem;
     constexpr int TX = 64, NT = TX * SEG, NWARP = NT / 32;
@@ -52,7 +57,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     // generic LD/ST instead of LDS/STS for every tile access
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_dyn);
-    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[2], uv_bar;
     __shared__ T sm_phi[PW * PH];
 
     const int W = a.w, H = a.h;
@@ -69,15 +74,29 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         tma_load_3d(&sm.raw[s][0][0], &maps.wf, x0 - 4, y0 - 4, c, &full_bar[s]);
         tma_load_3d(&sm.s1[s][0][0], &maps.s1, x0 - 4, y0 - 2, c, &full_bar[s]);
     };
+    // The u / v tiles of the Laplacian stage (halo 1; fetched as 72 x (TY+2) boxes at (x0-4, y0-1) for
+    // TMA's 16-byte coordinate rule) go into the input stage that the last-but-one channel releases,
+    // so their latency hides behind the last channel.  Only when no increment has to be added (du ==
+    // nullptr, i.e. every first inner iteration); otherwise the tiles are built with plain loads.
+    const bool uv_staged = a.du == nullptr;
+    const int su = C & 1;
+    static_assert(UH * RW <= RHt * RW && UH * RW <= SH * RW, "u / v boxes fit the released input stage");
+    auto issue_uv = [&]() {
+        mbar_expect_tx(&uv_bar, (uint32_t)(2 * sizeof(T) * UH * RW));
+        tma_load_2d(&sm.raw[su][0][0], &maps.u, x0 - 4, y0 - 1, &uv_bar);
+        tma_load_2d(&sm.s1[su][0][0], &maps.v, x0 - 4, y0 - 1, &uv_bar);
+    };
     if (tid == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
+        mbar_init(&uv_bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
         issue(0);
         if (C > 1) issue(1);
+        else if (uv_staged) issue_uv();   // a single channel never touches stage 1
     }
 
     // replicate-border fix-up of a tile whose entry (r, c) sits at image coordinate (oy + r, ox + c)
@@ -161,7 +180,10 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         if (tid < 4 * SEG) vstage(TX + (tid & 3), tid >> 2);
         __syncthreads();
         // both input stages of this channel are free: prefetch channel c+2 into them
-        if (tid == 0 && c + 2 < C) issue(c + 2);
+        if (tid == 0) {
+            if (c + 2 < C) issue(c + 2);
+            else if (c + 2 == C && uv_staged) issue_uv();
+        }
         if (border) {
             fixup(&sm.bl[0][0], SH, BW, BW, x0 - 2, y0 - 2);
             __syncthreads();
@@ -201,9 +223,9 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
 
     // ---- u+du, v+dv tiles (halo 1) -> phi on the tile plus its left/up halo; tiles reloaded with
     //      plain u, v when du is present: the Laplacian acts on u (S/OpticalFlow.cpp:437-438) ------
-    T* tu = &sm.hs[0][0];
-    T* tv = tu + UW * UH;
     T* tphi = sm_phi;
+    auto tail = [&](T* tu, T* tv, auto stride_c) {
+    constexpr int US = decltype(stride_c)::value;      // row stride of the u / v tiles; entry (uy, ux) is pixel (y0-1+uy, x0-1+ux)
     auto load_uv = [&](bool with_increment) {
         for (int uy = warp; uy < UH; uy += NWARP) {
             const size_t ro = (size_t)clampi(y0 - 1 + uy, H) * a.pitch;
@@ -211,24 +233,33 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
                 const size_t o = ro + clampi(x0 - 1 + ux, W);
                 T uv = a.u[o], vv = a.v[o];
                 if (with_increment) { uv += a.du[o]; vv += a.dv[o]; }
-                tu[uy * UW + ux] = uv;
-                tv[uy * UW + ux] = vv;
+                tu[uy * US + ux] = uv;
+                tv[uy * US + ux] = vv;
             }
         }
     };
-    load_uv(a.du != nullptr);
-    __syncthreads();
+    if (uv_staged) {
+        mbar_wait(&uv_bar, 0);
+        if (border) {                                   // replicate clamp over TMA's zero fill
+            fixup(tu - 3, UH, RW, RW, x0 - 4, y0 - 1);
+            fixup(tv - 3, UH, RW, RW, x0 - 4, y0 - 1);
+            __syncthreads();
+        }
+    } else {
+        load_uv(true);
+        __syncthreads();
+    }
     for (int py = warp; py < PH; py += NWARP) {
         const int Y = y0 - 1 + py;
         for (int px = lane; px < PW; px += 32) {
             const int X = x0 - 1 + px;
             T val = 0;
             if (X >= 0 && X < W && Y >= 0 && Y < H) {
-                const int ui = py * UW + px;
+                const int ui = py * US + px;
                 const T u0 = tu[ui], v0 = tv[ui];
                 T ux = 0, uy = 0, vx = 0, vy = 0;
                 if (X < W - 1) { ux = tu[ui + 1] - u0; vx = tv[ui + 1] - v0; }
-                if (Y < H - 1) { uy = tu[ui + UW] - u0; vy = tv[ui + UW] - v0; }
+                if (Y < H - 1) { uy = tu[ui + US] - u0; vy = tv[ui + US] - v0; }
                 const T t = ux * ux + uy * uy + vx * vx + vy * vy;
                 val = phi_of(t, a.eps);
             }
@@ -236,7 +267,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         }
     }
     __syncthreads();
-    if (a.du) {
+    if (!uv_staged) {
         load_uv(false);
         __syncthreads();
     }
@@ -247,7 +278,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     for (int k = 0; k < PPT; k++) {
         const int cy = seg * PPT + k, Y = y0 + cy, X = PX;
         if (Y >= H) continue;
-        const int pi = (cy + 1) * PW + (col + 1), ui = (cy + 1) * UW + (col + 1);
+        const int pi = (cy + 1) * PW + (col + 1), ui = (cy + 1) * US + (col + 1);
         const T ph = tphi[pi];
         const bool xr = X < W - 1, xl = X > 0, yd = Y < H - 1, yu = Y > 0;
         T lu = 0, lv = 0, cf = 0;
@@ -260,11 +291,11 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
             }
         }
         if (yd) {
-            lu -= (tu[ui + UW] - tu[ui]) * ph;
-            lv -= (tv[ui + UW] - tv[ui]) * ph;
+            lu -= (tu[ui + US] - tu[ui]) * ph;
+            lv -= (tv[ui + US] - tv[ui]) * ph;
             if (yu) {
-                lu += (tu[ui] - tu[ui - UW]) * tphi[pi - PW];
-                lv += (tv[ui] - tv[ui - UW]) * tphi[pi - PW];
+                lu += (tu[ui] - tu[ui - US]) * tphi[pi - PW];
+                lv += (tv[ui] - tv[ui - US]) * tphi[pi - PW];
             }
         }
         if (xl) cf += tphi[pi - 1];
@@ -286,6 +317,9 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         a.bu[o] = -a_tx - a.alpha * lu;
         a.bv[o] = -a_ty - a.alpha * lv;
     }
+    };
+    if (uv_staged) tail(&sm.raw[su][0][0] + 3, &sm.s1[su][0][0] + 3, std::integral_constant<int, RW>{});
+    else tail(&sm.hs[0][0], &sm.hs[0][0] + UW * UH, std::integral_constant<int, UW>{});
 }
 
 }  // namespace pf

@@ -248,10 +248,13 @@ __device__ __forceinline__ SamplePos sample_pos(int j, float f, int n, float& fr
     return p;
 }
 
-// One thread handles kWarpPix pixels 32 columns apart: the flow loads of all of them are issued
+// One thread handles kWarpPix pixels 32 columns apart (2 measured best, with 1/3/4 within 10 %): the flow loads of all of them are issued
 // first, then per channel all 4*kWarpPix gathers, so each thread keeps 16+ independent loads in
 // flight (the kernel is latency bound otherwise: two dependent memory round trips per pixel).
-constexpr int kWarpPix = 4;
+#ifndef PF_WARP_PIX
+#define PF_WARP_PIX 2
+#endif
+constexpr int kWarpPix = PF_WARP_PIX;
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
@@ -271,7 +274,8 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
             if (du) { uu[i] += du[of]; vv[i] += dv[of]; }
         }
     }
-    size_t o00[kWarpPix], o01[kWarpPix], o10[kWarpPix], o11[kWarpPix];
+    // element offsets inside one plane fit 32 bits (a 3840x2160 plane is 8.3 M elements)
+    int o00[kWarpPix], o01[kWarpPix], o10[kWarpPix], o11[kWarpPix];
     T w00[kWarpPix], w01[kWarpPix], w10[kWarpPix], w11[kWarpPix];
     bool inside[kWarpPix];
 #pragma unroll
@@ -293,20 +297,26 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
         const int x0 = clampi(px.i, W), x1 = clampi(px.i + 1, W), y0 = clampi(py.i, H), y1 = clampi(py.i + 1, H);
         const T ax0 = fabs((T)1 - fx), ax1 = fabs((T)0 - fx), ay0 = fabs((T)1 - fy), ay1 = fabs((T)0 - fy);
         w00[i] = ax0 * ay0; w01[i] = ax0 * ay1; w10[i] = ax1 * ay0; w11[i] = ax1 * ay1;
-        o00[i] = (size_t)y0 * im2.pitch + x0; o01[i] = (size_t)y1 * im2.pitch + x0;
-        o10[i] = (size_t)y0 * im2.pitch + x1; o11[i] = (size_t)y1 * im2.pitch + x1;
+        o00[i] = y0 * im2.pitch + x0; o01[i] = y1 * im2.pitch + x0;
+        o10[i] = y0 * im2.pitch + x1; o11[i] = y1 * im2.pitch + x1;
     }
-    for (int k = 0; k < im1.c; k++) {
+    const int orow1 = y * im1.pitch, orow_w = y * warp.pitch;
+    // the gathers of channel k+1 are issued before channel k is reduced and stored (two register
+    // buffers), so a thread has up to 8*kWarpPix loads in flight and the memory round trips of
+    // consecutive channels overlap instead of adding up
+    auto gather = [&](int k, T (&a)[4][kWarpPix]) {
         const T* p = im2.ch(k);
         const T* q = im1.ch(k);
-        T a00[kWarpPix], a01[kWarpPix], a10[kWarpPix], a11[kWarpPix];
 #pragma unroll
         for (int i = 0; i < kWarpPix; i++) {
             const int x = xb + 32 * i;
-            if (inside[i]) { a00[i] = p[o00[i]]; a01[i] = p[o01[i]]; a10[i] = p[o10[i]]; a11[i] = p[o11[i]]; }
-            else if (x < W) { a00[i] = q[(size_t)y * im1.pitch + x]; a01[i] = a10[i] = a11[i] = 0; }
-            else { a00[i] = a01[i] = a10[i] = a11[i] = 0; }
+            if (inside[i]) { a[0][i] = p[o00[i]]; a[1][i] = p[o01[i]]; a[2][i] = p[o10[i]]; a[3][i] = p[o11[i]]; }
+            else if (x < W) { a[0][i] = q[orow1 + x]; a[1][i] = a[2][i] = a[3][i] = 0; }
+            else { a[0][i] = a[1][i] = a[2][i] = a[3][i] = 0; }
         }
+    };
+    auto reduce = [&](int k, const T (&a)[4][kWarpPix]) {
+        T* o = warp.ch(k) + orow_w;
 #pragma unroll
         for (int i = 0; i < kWarpPix; i++) {
             const int x = xb + 32 * i;
@@ -314,16 +324,27 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
             T acc;
             if (inside[i]) {
                 acc = 0;
-                acc += a00[i] * w00[i];
-                acc += a01[i] * w01[i];
-                acc += a10[i] * w10[i];
-                acc += a11[i] * w11[i];
+                acc += a[0][i] * w00[i];
+                acc += a[1][i] * w01[i];
+                acc += a[2][i] * w10[i];
+                acc += a[3][i] * w11[i];
             } else {
-                acc = a00[i];          // Im1 fallback outside the image
+                acc = a[0][i];          // Im1 fallback outside the image
             }
-            warp.ch(k)[(size_t)y * warp.pitch + x] = acc;
+            o[x] = acc;
         }
+    };
+    const int C = im1.c;
+    T A[4][kWarpPix], B[4][kWarpPix];
+    gather(0, A);
+    int k = 0;
+    for (; k + 1 < C; k += 2) {
+        gather(k + 1, B);
+        reduce(k, A);
+        if (k + 2 < C) gather(k + 2, A);
+        reduce(k + 1, B);
     }
+    if (k < C) reduce(k, A);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -621,10 +642,17 @@ struct FusedArgs {
 // psi = 1 / (2 sqrt(t + eps)).  FP64 keeps the reference's expression; FP32 uses the hardware
 // reciprocal square root (2 ulp), far below the single-precision noise of the products it scales.
 __device__ __forceinline__ double psi_of(double t, double eps) { return 1.0 / (2.0 * sqrt(t + eps)); }
-__device__ __forceinline__ float psi_of(float t, float eps) { return 0.5f * rsqrtf(t + eps); }
+// t + eps >= 1e-6 is always a normal number, so the flush-to-zero form (one MUFU.RSQ, no denormal
+// pre/post-scaling) returns exactly what rsqrtf() would
+__device__ __forceinline__ float rsqrt_normal(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float psi_of(float t, float eps) { return 0.5f * rsqrt_normal(t + eps); }
 // the same split for phi = 0.5/sqrt(t+eps), the channel mean and omega/denominator
 __device__ __forceinline__ double phi_of(double t, double eps) { return 0.5 / sqrt(t + eps); }
-__device__ __forceinline__ float phi_of(float t, float eps) { return 0.5f * rsqrtf(t + eps); }
+__device__ __forceinline__ float phi_of(float t, float eps) { return 0.5f * rsqrt_normal(t + eps); }
 __device__ __forceinline__ double mean_of(double s, int c, double) { return s / (double)c; }
 __device__ __forceinline__ float mean_of(float s, int, float inv_c) { return s * inv_c; }
 __device__ __forceinline__ double ratio_of(double a, double b) { return a / b; }

@@ -635,6 +635,8 @@ class Plan : public PlanBase {
         if (fused_ && fused_tma_) {
             c.fmaps.wf = make_image_map(c.wf.p, w, h, fc_, c.wf.pitch, c.wf.plane, 72, kFTY + 8);
             c.fmaps.s1 = make_image_map(c.s1.p, w, h, fc_, c.s1.pitch, c.s1.plane, 72, kFTY + 4);
+            c.fmaps.u = make_plane_map(u_, w, h, pitch, 72, kFTY + 2);   // u_ / v_ are updated in place within a level
+            c.fmaps.v = make_plane_map(v_, w, h, pitch, 72, kFTY + 2);
         }
         c.pw = w;
         c.ph = h;
