@@ -30,6 +30,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# before ANY CUDA context exists (torch included): one hardware work queue per in-flight pair stream
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 
 H, W, CH = 1080, 1920, 3

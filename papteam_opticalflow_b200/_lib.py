@@ -32,6 +32,9 @@ def lib():
         raise ImportError(
             "%s is missing: build it with `python __graft_entry__.py` or "
             "`make -C papteam_opticalflow_b200/csrc` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    # hardware work queues for the one-stream-per-pair concurrency; read by the driver at context creation
+    # (the library's load-time constructor does the same -- this covers interpreters that fork workers)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     L = C.CDLL(LIB_PATH)
     i, d, v = C.c_int, C.c_double, C.c_void_p
     sig = {

@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/pyflow_b200.h.  Argument validation, error translation
 // and mode dispatch only; the work is in Plan<T> (solver.cuh) and Stages<T> (stages.cuh).
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -143,6 +144,13 @@ pf_plan* pool_acquire(const Params& p, int& rc) {
 }
 
 }  // namespace
+
+// Concurrent pairs run on one CUDA stream each.  The driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS
+// hardware work queues and streams that share a queue serialise (measured on B200, driver 580: the batch
+// entry point loses 13 % with the variable unset).  It is read when the CUDA context is created, so it is
+// set -- without overriding the user's choice -- when this library is loaded; a host process that created
+// its context earlier must export it itself.
+__attribute__((constructor)) static void pf_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 extern "C" {
 
@@ -371,6 +379,10 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     std::vector<std::string> messages((size_t)nworkers);
     std::vector<std::atomic<int>> next((size_t)ndevices);
     for (auto& n : next) n.store(0);
+    // PF_BATCH_TRACE=1: mean CUDA-event time of the three legs of a pair, printed to stderr (diagnostic)
+    const bool trace = getenv("PF_BATCH_TRACE") && atoi(getenv("PF_BATCH_TRACE"));
+    std::mutex trace_mu;
+    double trace_sum[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int wk = 0; wk < nworkers; wk++) {
         workers.emplace_back([&, wk]() {
             const int d = wk % ndevices;
@@ -382,7 +394,13 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                 int k = next[(size_t)d].fetch_add(1);
                 int p = d + k * ndevices;
                 if (p >= npairs) break;
-                r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], nullptr);
+                double t[PF_NUM_TIMINGS];
+                r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], trace ? t : nullptr);
+                if (trace && r == PF_OK) {
+                    std::lock_guard<std::mutex> lk(trace_mu);
+                    trace_sum[0] += t[PF_T_H2D]; trace_sum[1] += t[PF_T_SOLVE]; trace_sum[2] += t[PF_T_D2H]; trace_sum[3] += 1;
+                    trace_sum[4] += t[13]; trace_sum[5] += t[14]; trace_sum[6] += t[15];
+                }
             }
             if (r) messages[(size_t)wk] = g_err;
             if (pl) pool_release(pl);
@@ -390,7 +408,12 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
         });
     }
     for (auto& t : workers) t.join();
-    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (seconds) *seconds = secs;
+    if (trace && trace_sum[3] > 0)
+        fprintf(stderr, "[pf_batch_flow] %d pairs, %d workers, %.3f s: mean per pair H2D %.2f ms, solve %.2f ms, D2H %.2f ms; host: copy enqueue %.2f ms, "
+                "graph launch %.2f ms, whole call %.2f ms\n", npairs, nworkers, secs, trace_sum[0] / trace_sum[3], trace_sum[1] / trace_sum[3],
+                trace_sum[2] / trace_sum[3], trace_sum[4] / trace_sum[3], trace_sum[5] / trace_sum[3], trace_sum[6] / trace_sum[3]);
     for (int wk = 0; wk < nworkers; wk++)
         if (status[(size_t)wk]) return fail(status[(size_t)wk], messages[(size_t)wk]);
     return PF_OK;

@@ -3,6 +3,7 @@
 // (fast mode) and double (parity mode).  Host code only orchestrates: all arithmetic is in
 // kernels.cuh / sor.cuh.
 #pragma once
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <memory>
@@ -314,10 +315,13 @@ class Plan : public PlanBase {
     void execute(double* vx, double* vy, double* warp, const double* im1, const double* im2,
                  double* timings) override {
         PF_CUDA(cudaSetDevice(P.device));
+        const auto h0 = std::chrono::steady_clock::now();
         PF_CUDA(cudaEventRecord(ev_[0], st_));
         upload(im1, im2);
         PF_CUDA(cudaEventRecord(ev_[1], st_));
+        const auto h1 = std::chrono::steady_clock::now();
         run_solve();
+        const auto h2 = std::chrono::steady_clock::now();
         PF_CUDA(cudaEventRecord(ev_[2], st_));
         size_t n = (size_t)P.h * P.w * sizeof(double);
         PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
@@ -336,6 +340,10 @@ class Plan : public PlanBase {
             timings[PF_T_H2D] = b;
             timings[PF_T_SOLVE] = c;
             timings[PF_T_D2H] = d;
+            // host-side wall clock of the enqueue calls and of the whole call (diagnostics, ms)
+            timings[13] = std::chrono::duration<double, std::milli>(h1 - h0).count();
+            timings[14] = std::chrono::duration<double, std::milli>(h2 - h1).count();
+            timings[15] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         }
     }
 
