@@ -139,6 +139,83 @@ __global__ void __launch_bounds__(256) k_filter_hv(Img<T> src, Img<T> dst, Taps<
     }
 }
 
+// Same operation with COMPILE-TIME half-widths (the pyramid's Gaussians have half-widths 1..4, the
+// 5x5 smoothing 2, the bicubic gradients 1/0): taps come straight from the constant bank, the
+// horizontal pass computes four adjacent outputs from 16-byte shared-memory loads, the vertical pass
+// slides a register window down four rows.  Same term order as the generic kernel (ascending tap
+// index, accumulator starting at 0), so both produce identical bits; ~6x fewer instructions.
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+template <typename T, int FH, int FV>
+__global__ void __launch_bounds__(256) k_filter_hv_t(Img<T> src, Img<T> dst, const Taps<T> th, const Taps<T> tv) {
+    constexpr int TX = 64, TY = 16;
+    constexpr int NL = (4 + 2 * FH + 3) / 4;             // 4-element groups feeding four adjacent outputs
+    constexpr int RW = 60 + 4 * NL;                      // raw row stride: last group of the last column quad stays in the row
+    constexpr int RHt = TY + 2 * FV;
+    static_assert(RW >= TX + 2 * FH && RW % 4 == 0, "raw row holds the halo and keeps 16-byte alignment");
+    __shared__ __align__(16) T raw[RHt * RW];
+    __shared__ __align__(16) T hs[RHt * TX];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, k = blockIdx.z;
+    const int W = src.w, H = src.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T* sp = src.ch(k);
+    for (int ry = warp; ry < RHt; ry += 8) {
+        const T* row = sp + (size_t)clampi(y0 - FV + ry, H) * src.pitch;
+        for (int rx = lane; rx < RW; rx += 32) raw[ry * RW + rx] = row[clampi(x0 - FH + rx, W)];
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < RHt * (TX / 4); task += 256) {
+        const int ry = task / (TX / 4), cq = task % (TX / 4);
+        T win[4 * NL];
+#pragma unroll
+        for (int g = 0; g < NL; g++) {
+            T q[4];
+            ld4(&raw[ry * RW + 4 * cq + 4 * g], q);
+#pragma unroll
+            for (int e = 0; e < 4; e++) win[4 * g + e] = q[e];
+        }
+        T out[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            T acc = 0;
+#pragma unroll
+            for (int l = 0; l <= 2 * FH; l++) acc += win[j + l] * th.v[l];
+            out[j] = acc;
+        }
+        st4(&hs[ry * TX + 4 * cq], out);
+    }
+    __syncthreads();
+    const int cx = threadIdx.x & (TX - 1), seg = threadIdx.x / TX;     // 4 row segments of 4 rows
+    const int X = x0 + cx;
+    if (X >= W) return;
+    T win[4 + 2 * FV];
+#pragma unroll
+    for (int i = 0; i < 4 + 2 * FV; i++) win[i] = hs[(seg * 4 + i) * TX + cx];
+    T* dp = dst.ch(k) + X;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int Y = y0 + seg * 4 + j;
+        T acc = 0;
+#pragma unroll
+        for (int l = 0; l <= 2 * FV; l++) acc += win[j + l] * tv.v[l];
+        if (Y < H) dp[(size_t)Y * dst.pitch] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bilinear sampler (S/ImageProcessing.h:138-157).  Coordinates stay in double in BOTH modes
 // (x = j + u at j ~ 3840 has only 2.4e-4 px resolution in FP32): the integer

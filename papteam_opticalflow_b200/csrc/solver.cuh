@@ -491,7 +491,18 @@ class Plan : public PlanBase {
 
     // h then v pass in one kernel (no intermediate plane)
     void filter_hv(const Img<T>& s, const Img<T>& d, const Taps<T>& th, const Taps<T>& tv) {
-        k_filter_hv<T><<<dim3(ceil_div(s.w, 64), ceil_div(s.h, 16), s.c), 256, 0, st_>>>(s, d, th, tv);
+        const dim3 grid(ceil_div(s.w, 64), ceil_div(s.h, 16), s.c);
+#define PF_HV(FH, FV) k_filter_hv_t<T, FH, FV><<<grid, 256, 0, st_>>>(s, d, th, tv)
+        switch (th.half * 16 + tv.half) {      // half-widths the pipeline uses get straight-line kernels
+            case 0x11: PF_HV(1, 1); break;
+            case 0x22: PF_HV(2, 2); break;
+            case 0x33: PF_HV(3, 3); break;
+            case 0x44: PF_HV(4, 4); break;
+            case 0x10: PF_HV(1, 0); break;
+            case 0x01: PF_HV(0, 1); break;
+            default: k_filter_hv<T><<<grid, 256, 0, st_>>>(s, d, th, tv);
+        }
+#undef PF_HV
         launches_++;
     }
 
