@@ -370,7 +370,7 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     // H2D / solve / D2H legs of different pairs overlap and the latency-bound coarse levels of one
     // pair hide behind the bandwidth-bound fine levels of another.
     const char* env = getenv("PF_BATCH_STREAMS");
-    int per_dev = env ? atoi(env) : 3;
+    int per_dev = env ? atoi(env) : 8;
     if (per_dev < 1) per_dev = 1;
     if (mode_is_lex(mode)) per_dev = 1;   // cooperative launches do not overlap usefully
     const int nworkers = std::min(std::max(npairs, 1), ndevices * per_dev);
@@ -433,7 +433,7 @@ int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* 
     // contiguous chunks of the pair list per worker, so that inside a chunk every frame's pyramid is
     // built once and reused as the next pair's first image
     const char* env = getenv("PF_BATCH_STREAMS");
-    int per_dev = env ? atoi(env) : 4;
+    int per_dev = env ? atoi(env) : 8;
     if (per_dev < 1 || mode_is_lex(mode)) per_dev = 1;
     const int nworkers = std::max(1, std::min(npairs, ndevices * per_dev));
     std::vector<std::thread> workers;

@@ -3,6 +3,7 @@
 // (fast mode) and double (parity mode).  Host code only orchestrates: all arithmetic is in
 // kernels.cuh / sor.cuh.
 #pragma once
+#include <cstring>
 #include <chrono>
 #include <algorithm>
 #include <cmath>
@@ -80,23 +81,34 @@ Taps<T> make_taps(const double* v, int half) {
     return t;
 }
 
-// Sweeps fused per launch of the tile kernel: whole solve if the image fits one region, otherwise
-// the value minimising a two-term cost model (bytes per pass + instruction issue per half-sweep).
+// Sweeps fused per launch of the tile kernel: the whole solve if the image fits one region, otherwise
+// the value minimising a cost model fitted on B200 (tools/sor_sweep.py, tools/ablation.py): a tile
+// visit costs ~a cycles (stage -> registers, write-back, exposed TMA) plus ~b per half-sweep, a pass
+// costs `launch` cycles on top.  Two fits:
+//   throughput (default): SM time = tiles/148 x visit cost, small launch term -- what counts when many
+//       pairs are in flight and other streams fill the idle SMs of a small level (+6 % pairs/s);
+//   latency (PF_SOR_TUNE=latency): whole waves and the full launch/ramp cost of every pass -- it spreads
+//       small levels over all SMs with large halos and is ~8 % faster for ONE pair alone.
+// PF_SOR_MODEL=a:b:launch:kind (kind 1 = whole waves, 0 = at least one wave, 2 = SM time) overrides.
 inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced) {
     if (w <= kSorRegionW && h <= region_h) return nsor;
     if (forced > 0) return std::min(forced, nsor);
+    static double ma = -1, mb = 0, ml = 0, mkind = 2;
+    if (ma < 0) {
+        const char* tune = getenv("PF_SOR_TUNE");
+        if (tune && !strcmp(tune, "latency")) { ma = 5500; mb = 380; ml = 7200; mkind = 1; }
+        else { ma = 8000; mb = 380; ml = 1500; mkind = 2; }
+        if (const char* e = getenv("PF_SOR_MODEL")) sscanf(e, "%lf:%lf:%lf:%lf", &ma, &mb, &ml, &mkind);
+    }
     double best = 1e300;
     int best_t = 1;
     for (int t = 1; t <= std::min(nsor, 12); t++) {
         SorTiling tx = sor_tiling(w, kSorRegionW, 2 * t), ty = sor_tiling(h, region_h, 2 * t);
         if (tx.ntiles == 0 || ty.ntiles == 0) break;
-        double ctas = (double)tx.ntiles * ty.ntiles;
-        double waves = std::ceil(ctas / 148.0);
-        // fitted on B200 (tools/sor_sweep.py): a pass costs ~3.8 us of launch/ramp plus, per round of
-        // tiles, ~2.9 us (stage -> registers, write-back, TMA not yet hidden) + ~0.2 us per half-sweep
-        double per_round = 5500.0 + 2.0 * t * 380.0;
-        double passes = std::ceil((double)nsor / t);
-        double cost = passes * (waves * per_round + 7200.0);
+        const double ctas = (double)tx.ntiles * ty.ntiles;
+        const double waves = mkind == 1 ? std::ceil(ctas / 148.0) : mkind == 0 ? std::max(1.0, ctas / 148.0) : ctas / 148.0;
+        const double passes = std::ceil((double)nsor / t);
+        const double cost = passes * (waves * (ma + 2.0 * t * mb) + ml);
         if (cost < best) { best = cost; best_t = t; }
     }
     return best_t;
