@@ -137,6 +137,34 @@ int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* 
                         int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,
                         int mode, const int* devices, int ndevices, double* seconds);
 
+/* Output formats of a sequence (bytes per pixel crossing PCIe): */
+#define PF_SEQ_FLOW_F32 0 /* interleaved float32 (u, v), 8 B */
+#define PF_SEQ_FLOW_U16 1 /* the reference's 16-bit flow encoding, interleaved (u, v), 4 B */
+#define PF_SEQ_FLOW_BGR8 2 /* the reference driver's HSV flow visualisation as a BGR image, 3 B */
+
+/* the same sequence with every flow leaving the device in the reference's
+ * on-disk encoding, q = (unsigned short)((min(max(f,-200),200)+200)*160) evaluated in double
+ * (OpticalFlow::SaveOpticalFlow, S/OpticalFlow.cpp:993-1003; decoded by LoadOpticalFlow :962-975 as
+ * q/160-200): flows[t] receives h*w*2 unsigned shorts.  Half the D2H bytes of the float32 form. */
+int pf_sequence_flow_u8_u16(int nframes, const unsigned char* const* frames, unsigned short* const* flows,
+                            double alpha, double ratio, int minWidth, int levels, int nOuterFPIterations,
+                            int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,
+                            int mode, const int* devices, int ndevices, double* seconds);
+
+/* the same sequence with every flow leaving the device as the image the reference
+ * driver writes for it (generateOutputFlowImageFile, Par/OpticalFlowCalculation.py:143-162:
+ * cv2.cartToPolar -> hue = ang*180/pi/2, value = cv2.normalize(mag, 0..255, NORM_MINMAX), saturation 255
+ * -> cv2.cvtColor(HSV2BGR)), computed on the device from the float32 flow: images[t] receives h*w*3 bytes
+ * (BGR, what cv2.imwrite takes).  uint8 frames in, uint8 images out: 3/8 of the float32 D2H bytes. */
+int pf_sequence_flow_u8_bgr(int nframes, const unsigned char* const* frames, unsigned char* const* images,
+                            double alpha, double ratio, int minWidth, int levels, int nOuterFPIterations,
+                            int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,
+                            int mode, const int* devices, int ndevices, double* seconds);
+
+/* The visualisation alone, for callers of the pairwise entry points: flow is h*w interleaved float32
+ * (u, v) in host memory, bgr receives h*w*3 bytes. */
+int pf_flow_to_bgr(const float* flow, unsigned char* bgr, int h, int w, int device);
+
 /* ---- ONE large pair over several GPUs (BASELINE config 5): every device runs the
  * cheap stages redundantly, the SOR solve is split into row bands with peer-to-peer halo exchange
  * over NVLink after every fused-sweep pass (cudaMemcpyPeerAsync ordered by events, no collective).

@@ -203,6 +203,22 @@ def bicubic_warp(ref, im2, vx, vy):
     return out
 
 
+def flow_encode_u16(flow):
+    """S/OpticalFlow.cpp:993-1003 on any float64 array -> uint16 of the same shape."""
+    flow = _c(flow)
+    q = np.zeros(flow.shape, dtype=np.uint16)
+    lib().oracle_flow_encode_u16(q.ctypes.data_as(C.POINTER(C.c_ushort)), _p(flow), C.c_long(flow.size))
+    return q
+
+
+def flow_decode_u16(q):
+    """S/OpticalFlow.cpp:962-975."""
+    q = np.ascontiguousarray(q, dtype=np.uint16)
+    flow = np.zeros(q.shape)
+    lib().oracle_flow_decode_u16(_p(flow), q.ctypes.data_as(C.POINTER(C.c_ushort)), C.c_long(q.size))
+    return flow
+
+
 def coarse2fine_flow(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30,
                      colType=0, levels=0, order=LEX):
     """Upstream call shape (north_star); pass levels>0 for the fork's pyramidLevels shape."""

@@ -540,6 +540,26 @@ void oracle_bicubic_warp(double* out, const double* ref, const double* im2, cons
     free(ix); free(iy); free(ixy);
 }
 
+/* Flow file encoding.
+ * OpticalFlow::SaveOpticalFlow, S/OpticalFlow.cpp:993-1003:
+ *   foo[i] = (__min(__max(flow[i], -200), 200) + 200) * 160   -- double arithmetic, then the implicit
+ *   double -> unsigned short conversion (truncation; the value is within [0, 64000]).
+ * __max(a,b) is ((a)>(b)?(a):(b)): a NaN sample compares false and becomes -200 -> 0.
+ * OpticalFlow::LoadOpticalFlow, S/OpticalFlow.cpp:962-975: flow[i] = (double)foo[i] / 160 - 200. */
+void oracle_flow_encode_u16(unsigned short* q, const double* flow, long n) {
+    for (long i = 0; i < n; i++) {
+        double f = flow[i];
+        f = f > -200 ? f : -200;
+        f = f < 200 ? f : 200;
+        q[i] = (unsigned short)((f + 200) * 160);
+    }
+}
+
+void oracle_flow_decode_u16(double* flow, const unsigned short* q, long n) {
+    for (long i = 0; i < n; i++) flow[i] = (double)q[i] / 160 - 200;
+}
+
+
 /* --------------------------------------------------------------------------------------------
  * Whole solve.  Level loop S/OpticalFlow.cpp:735-846 with the parameters the fork hard-codes
  * (:747-751) exposed, and the level count either given (ConstructPyramidLevels) or derived from

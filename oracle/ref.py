@@ -69,6 +69,10 @@ class _Ref:
             L.ref_stage_gaussian.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double,
                                              C.c_int]
             L.ref_stage_bicubic.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int]
+            L.ref_save_optical_flow.argtypes = [_dp, C.c_int, C.c_int, C.c_char_p]
+            L.ref_save_optical_flow.restype = C.c_int
+            L.ref_load_optical_flow.argtypes = [_dp, C.c_int, C.c_int, C.c_char_p]
+            L.ref_load_optical_flow.restype = C.c_int
             L.ref_stage_smoothflow_sor.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
                                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                    C.c_int]
@@ -158,6 +162,20 @@ class _Ref:
         out = np.zeros((h, w, c))
         self.lib.ref_stage_gaussian(_p(out), _p(src), h, w, c, sigma, fsize)
         return out
+
+    def save_optical_flow(self, flow, path):
+        """OpticalFlow::SaveOpticalFlow (S/OpticalFlow.cpp:993-1003) on an (h, w, 2) float64 flow."""
+        flow = _c(flow)
+        h, w, _ = flow.shape
+        if not self.lib.ref_save_optical_flow(_p(flow), h, w, path.encode()):
+            raise IOError("reference SaveOpticalFlow failed")
+
+    def load_optical_flow(self, path, h, w):
+        """OpticalFlow::LoadOpticalFlow (S/OpticalFlow.cpp:962-975) -> (h, w, 2) float64."""
+        flow = np.zeros((h, w, 2))
+        if not self.lib.ref_load_optical_flow(_p(flow), h, w, path.encode()):
+            raise IOError("reference LoadOpticalFlow failed")
+        return flow
 
     def bicubic(self, ref, im2, vx, vy):
         ref, im2, vx, vy = _c(ref), _c(im2), _c(vx), _c(vy)

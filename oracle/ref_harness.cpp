@@ -234,6 +234,22 @@ void ref_stage_smoothflow_sor(const double* f1, const double* f2, double* warp, 
     store(u, U);
     store(v, V);
 }
+
+// Flow file format: the reference's own writer / reader, file in, file out.
+// flow is (h, w, 2) interleaved (u, v).  Returns 1 on success.
+int ref_save_optical_flow(const double* flow, int h, int w, const char* path) {
+    DImage F;
+    load(F, flow, h, w, 2);
+    return OpticalFlow::SaveOpticalFlow(F, path) ? 1 : 0;
+}
+
+int ref_load_optical_flow(double* flow, int h, int w, const char* path) {
+    DImage F;
+    if (!OpticalFlow::LoadOpticalFlow(path, F)) return 0;
+    if (F.height() != h || F.width() != w || F.nchannels() != 2) return 0;
+    store(flow, F);
+    return 1;
+}
 #endif  // !PAP_PARALLEL
 
 }  // extern "C"

@@ -61,6 +61,11 @@ def lib():
         "pf_batch_flow": (i, [i, dpp, dpp, dpp, dpp, dpp, d, d, i, i, i, i, i, i, i, i, i, i, ip, i, dp]),
         "pf_sequence_flow_u8": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_float)), d, d, i, i, i, i, i, i, i, i, i, i,
                                     ip, i, dp]),
+        "pf_sequence_flow_u8_u16": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_ushort)), d, d, i, i, i, i, i, i, i, i, i, i,
+                                        ip, i, dp]),
+        "pf_sequence_flow_u8_bgr": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_ubyte)), d, d, i, i, i, i, i, i, i, i, i, i,
+                                        ip, i, dp]),
+        "pf_flow_to_bgr": (i, [C.POINTER(C.c_float), C.POINTER(C.c_ubyte), i, i, i]),
         "pf_multigpu_flow": (i, [dp, dp, dp, dp, dp, d, d, i, i, i, i, i, i, i, i, i, ip, i, C.c_longlong, dp]),
         "pf_stage_pyramid": (i, [dp, dp, i, i, i, d, i, i, i]),
         "pf_stage_im2feature": (i, [dp, dp, i, i, i, i, i, i]),

@@ -419,9 +419,11 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     return PF_OK;
 }
 
-int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* const* flows, double alpha, double ratio,
-                        int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
-                        const int* devices, int ndevices, double* seconds) {
+}  // extern "C"
+
+static int sequence_flow(int format, int nframes, const unsigned char* const* frames, void* const* flows, double alpha, double ratio,
+                         int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
+                         const int* devices, int ndevices, double* seconds) {
     if (nframes < 0 || ndevices < 1 || !devices) return fail(PF_EINVAL, "bad sequence arguments");
     const int npairs = nframes > 0 ? nframes - 1 : 0;
     if (npairs > 0 && (!frames || !flows)) return fail(PF_EINVAL, "NULL argument");
@@ -449,7 +451,7 @@ int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* 
             if (rc == PF_OK) {
                 rc = guarded([&]() -> int {
                     pl->impl->seq_first(frames[p0]);
-                    for (int p = p0; p < p1; p++) pl->impl->seq_next(frames[p + 1], flows[p]);
+                    for (int p = p0; p < p1; p++) pl->impl->seq_next(frames[p + 1], flows[p], format);
                     return PF_OK;
                 });
             }
@@ -464,6 +466,67 @@ int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* 
         if (status[(size_t)wk]) return fail(status[(size_t)wk], messages[(size_t)wk]);
     return PF_OK;
 }
+
+int pf_sequence_flow_u8(int nframes, const unsigned char* const* frames, float* const* flows, double alpha, double ratio,
+                        int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
+                        const int* devices, int ndevices, double* seconds) {
+    return sequence_flow(PF_SEQ_FLOW_F32, nframes, frames, reinterpret_cast<void* const*>(flows), alpha, ratio, minWidth, levels, nOuter,
+                         nInner, nSOR, colType, h, w, c, mode, devices, ndevices, seconds);
+}
+
+int pf_sequence_flow_u8_bgr(int nframes, const unsigned char* const* frames, unsigned char* const* images, double alpha, double ratio,
+                            int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
+                            const int* devices, int ndevices, double* seconds) {
+    return sequence_flow(PF_SEQ_FLOW_BGR8, nframes, frames, reinterpret_cast<void* const*>(images), alpha, ratio, minWidth, levels, nOuter,
+                         nInner, nSOR, colType, h, w, c, mode, devices, ndevices, seconds);
+}
+
+int pf_flow_to_bgr(const float* flow, unsigned char* bgr, int h, int w, int device) {
+    if (!flow || !bgr) return fail(PF_EINVAL, "NULL argument");
+    int r;
+    if ((r = check_image(h, w, 1)) || (r = check_device(device))) return r;
+    return guarded([&]() -> int {
+        PF_CUDA(cudaSetDevice(device));
+        const size_t n = (size_t)h * w;
+        float* d_flow = nullptr;
+        unsigned char* d_out = nullptr;
+        unsigned int* d_mm = nullptr;
+        cudaStream_t st = nullptr;
+        auto cleanup = [&]() {
+            if (d_flow) cudaFree(d_flow);
+            if (d_out) cudaFree(d_out);
+            if (d_mm) cudaFree(d_mm);
+            if (st) cudaStreamDestroy(st);
+        };
+        try {
+            PF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            PF_CUDA(cudaMalloc(&d_flow, n * 2 * sizeof(float)));
+            PF_CUDA(cudaMalloc(&d_out, n * 3));
+            PF_CUDA(cudaMalloc(&d_mm, 2 * sizeof(unsigned int)));
+            PF_CUDA(cudaMemcpyAsync(d_flow, flow, n * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+            k_minmax_init<<<1, 1, 0, st>>>(d_mm);
+            k_flow_mag_minmax<float><<<dim3(ceil_div(w, 256), std::min(h, 256)), 256, 0, st>>>(d_flow, d_flow + 1, 2 * w, 2, w, h, d_mm);
+            k_flow_to_bgr<float><<<dim3(ceil_div(w, 128), h), 128, 0, st>>>(d_flow, d_flow + 1, 2 * w, 2, w, d_mm, d_out);
+            PF_CHECK_LAUNCH();
+            PF_CUDA(cudaMemcpyAsync(bgr, d_out, n * 3, cudaMemcpyDeviceToHost, st));
+            PF_CUDA(cudaStreamSynchronize(st));
+        } catch (...) {
+            cleanup();
+            throw;
+        }
+        cleanup();
+        return PF_OK;
+    });
+}
+
+int pf_sequence_flow_u8_u16(int nframes, const unsigned char* const* frames, unsigned short* const* flows, double alpha, double ratio,
+                            int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w, int c, int mode,
+                            const int* devices, int ndevices, double* seconds) {
+    return sequence_flow(PF_SEQ_FLOW_U16, nframes, frames, reinterpret_cast<void* const*>(flows), alpha, ratio, minWidth, levels, nOuter,
+                         nInner, nSOR, colType, h, w, c, mode, devices, ndevices, seconds);
+}
+
+extern "C" {
 
 int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2, double alpha,
                      double ratio, int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h, int w,

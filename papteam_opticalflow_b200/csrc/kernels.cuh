@@ -48,6 +48,119 @@ __global__ void k_export_flow_f32(const T* __restrict__ u, const T* __restrict__
     out[(size_t)y * w + x] = make_float2((float)u[(size_t)y * pitch + x], (float)v[(size_t)y * pitch + x]);
 }
 
+// The reference's 16-bit flow encoding (OpticalFlow::SaveOpticalFlow, S/OpticalFlow.cpp:993-1003):
+// q = (unsigned short)((min(max(f, -200), 200) + 200) * 160), evaluated in double, (u, v) interleaved.
+__device__ __forceinline__ unsigned short flow_to_u16(double f) {
+    f = fmin(fmax(f, -200.0), 200.0);
+    return (unsigned short)((f + 200.0) * 160.0);
+}
+template <typename T>
+__global__ void k_export_flow_u16(const T* __restrict__ u, const T* __restrict__ v, int pitch, int w, ushort2* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    out[(size_t)y * w + x] = make_ushort2(flow_to_u16((double)u[(size_t)y * pitch + x]), flow_to_u16((double)v[(size_t)y * pitch + x]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flow visualisation of the reference driver, generateOutputFlowImageFile,
+// Par/OpticalFlowCalculation.py:143-162: (mag, ang) = cv2.cartToPolar(u, v); H = ang*180/pi/2,
+// S = 255, V = cv2.normalize(mag, 0..255, NORM_MINMAX), both stored to uint8 by truncation;
+// BGR = cv2.cvtColor(hsv, COLOR_HSV2BGR).  OpenCV's arithmetic for these calls (float32 magnitude with
+// one FMA, fastAtan32f's degree polynomial with FMAs, float64 min-max scaling, float32 HSV sector
+// formula whose 8-bit results are truncated) is restated operation by operation with explicitly
+// rounded intrinsics, so nvcc can neither contract nor reorder anything (the tests hold a numpy
+// restatement of the same operations that is pinned against cv2 4.13).
+// Two kernels: a min/max reduction of the magnitude (non-negative floats order like their bit
+// patterns, so atomicMin/atomicMax on the bits), then the per-pixel conversion.
+// Inputs are addressed as base[y*pitch + x*stride]: planar solver planes (stride 1) or an
+// interleaved (u, v) host layout (stride 2, v = u + 1).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float flow_mag(float x, float y) { return __fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(y, y))); }
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, k), p3 = __fmul_rn(-0.3258083974640975f, k);
+    const float p5 = __fmul_rn(0.1555786518463281f, k), p7 = __fmul_rn(-0.04432655554792128f, k);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float c = __fdiv_rn(fminf(ax, ay), __fadd_rn(fmaxf(ax, ay), 2.220446049250313e-16f));
+    const float c2 = __fmul_rn(c, c);
+    float a = __fmaf_rn(c2, p7, p5);
+    a = __fmaf_rn(a, c2, p3);
+    a = __fmaf_rn(a, c2, p1);
+    a = __fmul_rn(a, c);
+    if (!(ax >= ay)) a = __fsub_rn(90.f, a);
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+static __global__ void k_minmax_init(unsigned int* mm) {
+    mm[0] = 0x7f800000u;   // +inf
+    mm[1] = 0u;
+}
+
+template <typename T>
+__global__ void k_flow_mag_minmax(const T* __restrict__ u, const T* __restrict__ v, int pitch, int stride, int w, int h,
+                                  unsigned int* __restrict__ mm) {
+    unsigned int lo = 0x7f800000u, hi = 0u;
+    for (int y = blockIdx.y; y < h; y += gridDim.y)
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+            const size_t o = (size_t)y * pitch + (size_t)x * stride;
+            const unsigned int b = __float_as_uint(flow_mag((float)u[o], (float)v[o]));
+            lo = min(lo, b);
+            hi = max(hi, b);
+        }
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+
+template <typename T>
+__global__ void k_flow_to_bgr(const T* __restrict__ u, const T* __restrict__ v, int pitch, int stride, int w,
+                              const unsigned int* __restrict__ mm, unsigned char* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t o = (size_t)y * pitch + (size_t)x * stride;
+    const float fx = (float)u[o], fy = (float)v[o];
+    // hue byte: ang * 180 / pi / 2 in double, truncated
+    const float rad = __fmul_rn(fast_atan2_deg(fy, fx), (float)(3.14159265358979323846 / 180.0));
+    const double hd = __ddiv_rn(__ddiv_rn(__dmul_rn((double)rad, 180.0), 3.14159265358979323846), 2.0);
+    const int H = (int)hd & 255;
+    // value byte: min-max scaling to 0..255 in double, truncated
+    const double smin = (double)__uint_as_float(mm[0]), smax = (double)__uint_as_float(mm[1]);
+    const double range = __dsub_rn(smax, smin);
+    const double scale = __dmul_rn(255.0, range > 2.220446049250313e-16 ? __ddiv_rn(1.0, range) : 0.0);
+    const double shift = __dsub_rn(0.0, __dmul_rn(smin, scale));
+    const int V = (int)__dadd_rn(__dmul_rn((double)flow_mag(fx, fy), scale), shift) & 255;
+    // 8-bit HSV -> BGR, hue range 180, S = 255
+    float hh = __fmul_rn((float)H, 6.0f / 180.0f);
+    const float s = __fmul_rn(255.f, 1.0f / 255.0f), val = __fmul_rn((float)V, 1.0f / 255.0f);
+    if (hh >= 6.f) hh = __fsub_rn(hh, 6.f);
+    const int sector = (int)floorf(hh);
+    const float f = __fsub_rn(hh, (float)sector);
+    const float t0 = val, t1 = __fmul_rn(val, __fsub_rn(1.f, s));
+    const float t2 = __fmul_rn(val, __fsub_rn(1.f, __fmul_rn(s, f)));
+    const float t3 = __fmul_rn(val, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, f))));
+    float b, g, r;
+    switch (sector) {
+        case 0: b = t1; g = t3; r = t0; break;
+        case 1: b = t1; g = t0; r = t2; break;
+        case 2: b = t3; g = t0; r = t1; break;
+        case 3: b = t0; g = t2; r = t1; break;
+        case 4: b = t0; g = t1; r = t3; break;
+        default: b = t2; g = t1; r = t0; break;
+    }
+    unsigned char* q = out + ((size_t)y * w + x) * 3;
+    q[0] = (unsigned char)(int)__fmul_rn(b, 255.f);
+    q[1] = (unsigned char)(int)__fmul_rn(g, 255.f);
+    q[2] = (unsigned char)(int)__fmul_rn(r, 255.f);
+}
+
 template <typename T>
 __global__ void k_fill(Img<T> img, T value) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;

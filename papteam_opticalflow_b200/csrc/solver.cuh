@@ -31,7 +31,7 @@ struct PlanBase {
     virtual int level_timings(double* out, int max_levels) const = 0;
     virtual void solve_async(int repeats) = 0;   // enqueue only
     virtual void seq_first(const unsigned char* frame) = 0;
-    virtual void seq_next(const unsigned char* frame, float* flow) = 0;
+    virtual void seq_next(const unsigned char* frame, void* out, int format) = 0;   // format: PF_SEQ_*
     virtual cudaStream_t stream() const = 0;
     virtual int device() const = 0;
 };
@@ -287,7 +287,7 @@ class Plan : public PlanBase {
     ~Plan() override {
         cudaSetDevice(P.device);
         if (gexec_) cudaGraphExecDestroy(gexec_);
-        for (auto& g : gexec_seq_) if (g) cudaGraphExecDestroy(g);
+        for (auto& gp : gexec_seq_) for (auto& g : gp) if (g) cudaGraphExecDestroy(g);
         if (graph_) cudaGraphDestroy(graph_);
         for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
         for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
@@ -437,7 +437,7 @@ class Plan : public PlanBase {
         total += 3 * Arena::need(pl0 * P.c, sizeof(T));                  // bicubic ix, iy, ixy
         total += 10 * Arena::need(pl0 * fc_, sizeof(T));                 // f1 f2 wf s1 s2 tmp blend dx dy dt
         total += 16 * Arena::need(pl0, sizeof(T));                       // scalar planes
-        total += Arena::need(64, sizeof(double)) * 2 + Arena::need(1, sizeof(BicubicTable));
+        total += Arena::need(64, sizeof(double)) * 3 + Arena::need(1, sizeof(BicubicTable));
         arena_.reserve(total + 4096);
         d_in1_ = arena_.take<double>(in_elems);
         d_in2_ = arena_.take<double>(in_elems);
@@ -463,6 +463,7 @@ class Plan : public PlanBase {
         d_lap_ = arena_.take<double>(64);
         d_acc_ = arena_.take<double>(64);
         d_tab_ = arena_.take<BicubicTable>(1);
+        d_mm_ = reinterpret_cast<unsigned int*>(arena_.take<double>(64));   // magnitude min / max of the flow visualisation
         BicubicTable tab = make_bicubic_table();
         PF_CUDA(cudaMemcpy(d_tab_, &tab, sizeof(tab), cudaMemcpyHostToDevice));
         PF_CUDA(cudaMemset(d_acc_, 0, 64 * sizeof(double)));
@@ -800,19 +801,20 @@ class Plan : public PlanBase {
         PF_CHECK_LAUNCH();
     }
 
-    void seq_next(const unsigned char* frame, float* flow) override {
+    void seq_next(const unsigned char* frame, void* out, int format) override {
+        if (format < 0 || format >= kSeqFormats) throw Error(PF_EINVAL, "unknown sequence output format");
         PF_CUDA(cudaSetDevice(P.device));
         std::swap(pyr1_, pyr2_);            // the newer frame of the previous pair becomes Im1
         seq_parity_ ^= 1;
         size_t n = (size_t)P.h * P.w * P.c;
         PF_CUDA(cudaMemcpyAsync(d_in1_, frame, n, cudaMemcpyHostToDevice, st_));
         if (use_graph_) {
-            cudaGraphExec_t& ge = gexec_seq_[seq_parity_];
+            cudaGraphExec_t& ge = gexec_seq_[seq_parity_][format];
             if (!ge) {
                 cudaGraph_t g = nullptr;
                 PF_CUDA(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
                 try {
-                    enqueue_seq_pair();
+                    enqueue_seq_pair(format);
                 } catch (...) {
                     cudaStreamEndCapture(st_, &g);
                     if (g) cudaGraphDestroy(g);
@@ -824,21 +826,33 @@ class Plan : public PlanBase {
             }
             PF_CUDA(cudaGraphLaunch(ge, st_));
         } else {
-            enqueue_seq_pair();
+            enqueue_seq_pair(format);
         }
-        PF_CUDA(cudaMemcpyAsync(flow, d_vx_, (size_t)P.h * P.w * sizeof(float2), cudaMemcpyDeviceToHost, st_));
+        PF_CUDA(cudaMemcpyAsync(out, d_vx_, (size_t)P.h * P.w * seq_bytes_per_pixel(format), cudaMemcpyDeviceToHost, st_));
         PF_CUDA(cudaStreamSynchronize(st_));
     }
 
   private:
-    void enqueue_seq_pair() {
+    static size_t seq_bytes_per_pixel(int format) {
+        return format == PF_SEQ_FLOW_U16 ? sizeof(ushort2) : format == PF_SEQ_FLOW_BGR8 ? 3 : sizeof(float2);
+    }
+    void enqueue_seq_pair(int format) {
         ph_ctx();
         k_import_u8<T><<<grid2(P.w, P.h), 128, 0, st_>>>(reinterpret_cast<const unsigned char*>(d_in1_), pyr2_[0]);
         launches_++;
         ph_pyramid(1);
         ph_lap_init();
         ph_levels();
-        k_export_flow_f32<T><<<grid2(P.w, P.h), 128, 0, st_>>>(u_, v_, pitch_for(P.w), P.w, reinterpret_cast<float2*>(d_vx_));
+        if (format == PF_SEQ_FLOW_BGR8) {
+            const int pitch = pitch_for(P.w);
+            k_minmax_init<<<1, 1, 0, st_>>>(d_mm_);
+            k_flow_mag_minmax<T><<<dim3(ceil_div(P.w, 256), std::min(P.h, 256)), 256, 0, st_>>>(u_, v_, pitch, 1, P.w, P.h, d_mm_);
+            k_flow_to_bgr<T><<<grid2(P.w, P.h), 128, 0, st_>>>(u_, v_, pitch, 1, P.w, d_mm_, reinterpret_cast<unsigned char*>(d_vx_));
+            launches_ += 2;
+        } else if (format == PF_SEQ_FLOW_U16)
+            k_export_flow_u16<T><<<grid2(P.w, P.h), 128, 0, st_>>>(u_, v_, pitch_for(P.w), P.w, reinterpret_cast<ushort2*>(d_vx_));
+        else
+            k_export_flow_f32<T><<<grid2(P.w, P.h), 128, 0, st_>>>(u_, v_, pitch_for(P.w), P.w, reinterpret_cast<float2*>(d_vx_));
         launches_++;
         ph_restore();
     }
@@ -887,7 +901,9 @@ class Plan : public PlanBase {
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t gexec_ = nullptr;
-    cudaGraphExec_t gexec_seq_[2] = {nullptr, nullptr};
+    static constexpr int kSeqFormats = 3;
+    cudaGraphExec_t gexec_seq_[2][kSeqFormats] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    unsigned int* d_mm_ = nullptr;
     int seq_parity_ = 0;
     std::vector<Span> spans_;
     std::vector<double> level_ms_;

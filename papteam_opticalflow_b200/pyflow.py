@@ -212,15 +212,29 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
     return vx, vy, wi
 
 
+_SEQ_OUTPUTS = {"float32": (np.float32, C.c_float, 2, "pf_sequence_flow_u8"),
+                "u16": (np.uint16, C.c_ushort, 2, "pf_sequence_flow_u8_u16"),
+                "bgr8": (np.uint8, C.c_ubyte, 3, "pf_sequence_flow_u8_bgr")}
+
+
 def sequence_flow(frames, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7, nInnerFPIterations=1,
-                  nSORIterations=30, colType=0, levels=0, mode=None, devices=None):
-    """Flows of the consecutive pairs of a frame sequence (SURVEY.md 8f rows f1/f2).
+                  nSORIterations=30, colType=0, levels=0, mode=None, devices=None, output="float32", outs=None):
+    """Flows of the consecutive pairs of a frame sequence (SURVEY.md 8f rows f1/f2/f3).
 
     frames: list of (h, w, c) uint8 C-contiguous arrays (what PIL decodes; the reference driver converts
     them with astype(float)/255. before calling pyflow -- here that happens on the device).
-    Returns ([flow_0, ..., flow_{n-2}], seconds) with flow_t an (h, w, 2) float32 array (u, v) of pair
-    (t, t+1), equal to coarse2fine_flow(frames[t]/255., frames[t+1]/255., ...) cast to float32."""
+    Returns ([out_0, ..., out_{n-2}], seconds), out_t belonging to pair (t, t+1):
+      output="float32": (h, w, 2) float32 (u, v), equal to coarse2fine_flow(frames[t]/255., frames[t+1]/255., ...)
+                        cast to float32;
+      output="u16":     (h, w, 2) uint16 in the reference's flow-file encoding (S/OpticalFlow.cpp:993-1003; see
+                        decode_flow_u16 / save_flow_u16);
+      output="bgr8":    (h, w, 3) uint8, the HSV flow image the reference driver writes with cv2.imwrite
+                        (Par/OpticalFlowCalculation.py:143-162), see flow_to_bgr.
+    outs: optional preallocated (e.g. pinned) output arrays."""
     L = _lib.lib()
+    if output not in _SEQ_OUTPUTS:
+        raise ValueError("output must be one of %s" % sorted(_SEQ_OUTPUTS))
+    dt, ct, nch, fname = _SEQ_OUTPUTS[output]
     n = len(frames)
     if n < 2:
         return [], 0.0
@@ -232,15 +246,70 @@ def sequence_flow(frames, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIteratio
     if devices is None:
         devices = list(range(max(1, L.pf_device_count())))
     h, w, c = frames[0].shape
-    flows = [np.zeros((h, w, 2), dtype=np.float32) for _ in range(n - 1)]
+    if outs is None:
+        res = [np.zeros((h, w, nch), dtype=dt) for _ in range(n - 1)]
+    else:
+        res = list(outs)
+        if len(res) != n - 1 or any(o.dtype != dt or o.shape != (h, w, nch) or not o.flags["C_CONTIGUOUS"] for o in res):
+            raise ValueError("outs must be %d C-contiguous (h, w, %d) %s arrays" % (n - 1, nch, np.dtype(dt).name))
     fp = (C.POINTER(C.c_ubyte) * n)(*[f.ctypes.data_as(C.POINTER(C.c_ubyte)) for f in frames])
-    op = (C.POINTER(C.c_float) * (n - 1))(*[f.ctypes.data_as(C.POINTER(C.c_float)) for f in flows])
+    op = (C.POINTER(ct) * (n - 1))(*[f.ctypes.data_as(C.POINTER(ct)) for f in res])
     dev = (C.c_int * len(devices))(*devices)
     secs = C.c_double()
-    check(L.pf_sequence_flow_u8(n, fp, op, float(alpha), float(ratio), int(minWidth), int(levels), int(nOuterFPIterations),
-                                int(nInnerFPIterations), int(nSORIterations), int(colType), h, w, c, _mode_id(mode), dev,
-                                len(devices), C.byref(secs)))
-    return flows, secs.value
+    check(getattr(L, fname)(n, fp, op, float(alpha), float(ratio), int(minWidth), int(levels), int(nOuterFPIterations),
+                            int(nInnerFPIterations), int(nSORIterations), int(colType), h, w, c, _mode_id(mode), dev,
+                            len(devices), C.byref(secs)))
+    return res, secs.value
+
+
+def flow_to_bgr(flow, v=None, device=0):
+    """The reference driver's flow visualisation on the device (Par/OpticalFlowCalculation.py:143-162 up to, not
+    including, cv2.imwrite): flow_to_bgr(flow(h, w, 2)) or flow_to_bgr(u, v) -> (h, w, 3) uint8 BGR.
+    The flow is taken in float32 (cv2.cartToPolar itself computes in float32)."""
+    if v is not None:
+        flow = np.stack([np.asarray(flow), np.asarray(v)], axis=-1)
+    flow = np.ascontiguousarray(flow, dtype=np.float32)
+    if flow.ndim != 3 or flow.shape[2] != 2:
+        raise ValueError("flow must be (h, w, 2)")
+    h, w, _ = flow.shape
+    out = np.zeros((h, w, 3), dtype=np.uint8)
+    check(_lib.lib().pf_flow_to_bgr(flow.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_ubyte)), h, w,
+                                    int(device)))
+    return out
+
+
+# ---- the reference's flow file format (SURVEY.md 8f row f3) -- host-side container I/O only; the encoding
+#      itself is produced on the device by sequence_flow(encoded=True) ------------------------------------
+def decode_flow_u16(q):
+    """OpticalFlow::LoadOpticalFlow (S/OpticalFlow.cpp:962-975): f = (double)q / 160 - 200."""
+    return np.asarray(q, dtype=np.float64) / 160 - 200
+
+
+def save_flow_u16(path, q):
+    """Write an encoded (h, w, 2) uint16 flow as the reference's Image<unsigned short>::saveImage container
+    (S/Image.h:825-836): 16 bytes of type tag (g++'s typeid(unsigned short).name() = "t", zero padded here --
+    the reference leaves the 14 trailing bytes uninitialised), int32 width, height, channels, one bool
+    IsDerivativeImage (0), then the samples, all little endian."""
+    q = np.ascontiguousarray(q, dtype=np.uint16)
+    if q.ndim != 3 or q.shape[2] != 2:
+        raise ValueError("encoded flow must be (h, w, 2) uint16")
+    with open(path, "wb") as f:
+        f.write(b"t".ljust(16, b"\0"))
+        f.write(np.array([q.shape[1], q.shape[0], 2], dtype="<i4").tobytes())
+        f.write(b"\0")
+        f.write(q.astype("<u2").tobytes())
+
+
+def load_flow_u16(path):
+    """Read a file written by save_flow_u16 or by the reference's SaveOpticalFlow; returns (h, w, 2) uint16."""
+    with open(path, "rb") as f:
+        f.read(16)                                  # type tag: only its first byte(s) are defined
+        w, h, c = np.frombuffer(f.read(12), dtype="<i4")
+        f.read(1)
+        q = np.frombuffer(f.read(int(w) * int(h) * int(c) * 2), dtype="<u2")
+    if c != 2 or q.size != w * h * c:
+        raise ValueError("not an encoded two-channel flow file")
+    return q.reshape(int(h), int(w), 2).copy()
 
 
 def coarse2fine_flow_multigpu(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,

@@ -359,3 +359,57 @@ def test_sequence_mode_argument_errors():
         pyflow.sequence_flow([f, f.astype(float)])
     with pytest.raises(ValueError):
         pyflow.sequence_flow([f, f[:-1]])
+
+
+def test_sequence_mode_encoded_flow_matches_oracle_encoding(oracle_mod):
+    """flows leave the device in the reference's 16-bit encoding; bit-exact against
+    the oracle's encoder applied to the float32 flow of the same sequence; decodes to within 1/160 px."""
+    frames = [_u8_frame(240, i) for i in (1, 2, 30, 31)]
+    f32, _ = pyflow.sequence_flow(frames, devices=[0])
+    enc, _ = pyflow.sequence_flow(frames, devices=[0], output="u16")
+    assert len(enc) == 3
+    for q, f in zip(enc, f32):
+        assert q.dtype == np.uint16 and q.shape == f.shape
+        assert np.array_equal(q, oracle_mod.flow_encode_u16(f.astype(np.float64)))
+        d = pyflow.decode_flow_u16(q)
+        assert np.abs(d - f).max() <= 1 / 160 + 1e-6
+    # preallocated outputs, two chunks on the same device listed twice
+    outs = [np.zeros((135, 240, 2), np.uint16) for _ in range(3)]
+    got, _ = pyflow.sequence_flow(frames, devices=[0, 0], output="u16", outs=outs)
+    assert all(a is b for a, b in zip(got, outs)) and all(np.array_equal(a, b) for a, b in zip(outs, enc))
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow(frames, output="u16", outs=[np.zeros((135, 240, 2), np.float32)] * 3)
+
+
+def test_flow_visualisation_matches_cv2_golden_and_oracle():
+    """the driver's HSV flow image computed on the device.  Bit-exact against the numpy
+    restatement (same operations, same roundings) and therefore against cv2's golden HSV; BGR equals cv2's
+    wherever cv2 runs its vector body (+-1 in its scalar row tail, which rounds instead of truncating)."""
+    from oracle import flowvis as fv
+    g = golden("flowvis.npz")
+    for name in ("a", "b", "c", "zero"):
+        flow = g["flow_" + name]
+        got = pyflow.flow_to_bgr(flow)
+        assert got.dtype == np.uint8 and got.shape == flow.shape[:2] + (3,)
+        assert np.array_equal(got, fv.flow_to_bgr(flow.astype(np.float64))), name
+        want = g["bgr_" + name]
+        body = want.shape[1] & ~63
+        assert np.array_equal(got[:, :body], want[:, :body])
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+    u, v = g["flow_a"][..., 0], g["flow_a"][..., 1]
+    assert np.array_equal(pyflow.flow_to_bgr(u.astype(np.float64), v.astype(np.float64)), pyflow.flow_to_bgr(g["flow_a"]))
+    with pytest.raises(ValueError):
+        pyflow.flow_to_bgr(np.zeros((4, 4, 3), np.float32))
+
+
+def test_sequence_mode_bgr_output_is_the_visualisation_of_its_flow():
+    frames = [_u8_frame(240, i) for i in (1, 2, 30, 31)]
+    f32, _ = pyflow.sequence_flow(frames, devices=[0])
+    img, _ = pyflow.sequence_flow(frames, devices=[0], output="bgr8")
+    assert len(img) == 3
+    for im, f in zip(img, f32):
+        assert im.dtype == np.uint8 and im.shape == (135, 240, 3)
+        assert np.array_equal(im, pyflow.flow_to_bgr(f))
+        assert im.max() == 255              # min-max normalisation: the fastest pixel has full value
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow(frames, output="png")

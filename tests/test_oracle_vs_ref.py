@@ -73,3 +73,17 @@ def test_full_edge_cases(oracle_mod, ref_serial, case):
     assert eq(rx, ox) and eq(ry, oy) and eq(rw, ow)
     if case == "identical":
         assert np.abs(ox).max() == 0 and np.abs(oy).max() == 0
+
+
+def test_flow_file_round_trip_through_the_reference(oracle_mod, ref_serial, tmp_path):
+    """Files written by the product's container code load in the reference's LoadOpticalFlow, and the
+    reference's SaveOpticalFlow output equals the oracle's encoding (random + edge values)."""
+    import pyflow
+    rng = np.random.default_rng(3)
+    flow = rng.uniform(-260, 260, (17, 23, 2))
+    p1, p2 = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    ref_serial.save_optical_flow(flow, p1)
+    q = oracle_mod.flow_encode_u16(flow)
+    assert np.array_equal(pyflow.load_flow_u16(p1), q)
+    pyflow.save_flow_u16(p2, q)
+    assert np.array_equal(ref_serial.load_optical_flow(p2, 17, 23), oracle_mod.flow_decode_u16(q))

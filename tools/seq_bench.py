@@ -23,3 +23,10 @@ for streams in ("4", "8", "16"):
     flows, secs = pyflow.sequence_flow(fr, mode="fp32_redblack", devices=[0])
     dt = time.perf_counter() - t0
     print("streams", streams, "sequence: %.1f pairs/s (wall %.3f s, lib %.3f s)" % ((n - 1) / dt, dt, secs), flush=True)
+os.environ["PF_BATCH_STREAMS"] = "8"
+for output in ("float32", "u16", "bgr8"):
+    pyflow.sequence_flow(fr[:17], mode="fp32_redblack", devices=[0], output=output)
+    t0 = time.perf_counter()
+    pyflow.sequence_flow(fr, mode="fp32_redblack", devices=[0], output=output)
+    dt = time.perf_counter() - t0
+    print("output %-8s %.1f pairs/s" % (output, (n - 1) / dt), flush=True)
