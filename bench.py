@@ -12,7 +12,7 @@ Rank 0 prints exactly one JSON line (see the task contract):
   value      pairs/s, inputs resident in HBM, K graph replays timed with CUDA events on the
              launching stream, max over ranks
   e2e        pairs/s through the public plan API with HOST (pinned) buffers: H2D + solve + D2H per step
-  roofline   SOR kernel (k_sor_rb_tile) at pyramid level 0: algorithmic bytes (40 B per pixel-sweep in
+  roofline   SOR kernel (k_sor_rb_tma) at pyramid level 0: algorithmic bytes (40 B per pixel-sweep in
              FP32) / CUDA-event time of its launches, against the measured HBM peak
   cpu_baseline  the unmodified reference (oracle/_ref, Serial build, 1 core) on a bounded sample
 --impl reference times the reference's own OpenMP build on all host cores on the same workload
@@ -234,8 +234,36 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier(dist)
     e2e_s = dist_max(dist, local, e2e_s)
-    clocks = sampler.summary()
     e2e = args.gpus * args.steps * B / e2e_s
+
+    # ---- sequence mode (reported beside the headline, not instead of it): K*B+1 uint8
+    #      frames in, K*B float32 flows out, every frame's pyramid built once, conversion from uint8 on the device ----
+    def pinned_raw(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = lib.pf_host_alloc(nbytes)
+        if not ptr:
+            return np.zeros(shape, dtype)
+        return np.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=dtype).reshape(shape)
+    u8 = []
+    for f in frames:
+        a = pinned_raw(f.shape, np.uint8)
+        a[...] = np.rint(f * 255.0).astype(np.uint8)
+        u8.append(a)
+    seq_outs = [pinned_raw((H, W, 2), np.float32) for _ in range(ring)]
+    def seq_run(nsteps):
+        n = nsteps * B
+        pyflow.sequence_flow([u8[i % 3] for i in range(n + 1)], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"], PARAMS["nOuter"],
+                             PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"], mode=args.mode, devices=[local],
+                             outs=[seq_outs[i % ring] for i in range(n)])
+    seq_run(max(1, min(2, args.warmup)))
+    barrier(dist)
+    t0 = time.perf_counter()
+    seq_run(args.steps)
+    seq_s = time.perf_counter() - t0
+    barrier(dist)
+    seq_s = dist_max(dist, local, seq_s)
+    clocks = sampler.summary()
+    seq = args.gpus * args.steps * B / seq_s
 
     line = None
     if rank == 0:
@@ -279,9 +307,12 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * 2 * H * W * CH * 8),
                     "d2h_bytes_per_step": int(B * (2 * H * W + H * W * CH) * 8), "ms_per_step": 1000 * e2e_s / args.steps,
                     "api": "pyflow.coarse2fine_flow_batch -> pf_batch_flow (host float64 HWC in, host float64 out)"},
+            "e2e_sequence": {"value": seq, "unit": "pairs/s", "h2d_bytes_per_step": B * H * W * CH, "d2h_bytes_per_step": B * H * W * 8,
+                             "api": "pyflow.sequence_flow -> pf_sequence_flow_u8 (host uint8 frames in, host float32 (u,v) out; consecutive "
+                                    "pairs share a frame, its pyramid is built once)"},
             "gpu_launches": int(cnt[0]) * args.steps * B,
             "single_pair_latency_ms": single_ms,
-            "roofline": {"bound": "hbm", "kernel": "k_sor_rb_tile (level 0, 1920x1080)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_sor_rb_tma (level 0, 1920x1080)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_solve_level0": int(sor_launch_l0),
                          "avg_launch_ms": sor_ms_l0 / max(1.0, sor_launch_l0),
