@@ -31,7 +31,7 @@ struct FusedSmem {
     static constexpr int TX = 64, RW = 72, RH = TY + 8, SH = TY + 4, HW = 68, BW = 68;
     alignas(128) T raw[2][RH][RW];   // TMA destinations
     alignas(128) T s1[2][SH][RW];
-    T hs[RH][HW];
+    alignas(16) T hs[RH][HW];
     T bl[SH][BW];
     T dt[TY][TX];
 };
@@ -46,7 +46,6 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     constexpr int TX = 64, NT = TX * SEG, NWARP = NT / 32;
     constexpr int RW = Smem::RW, RHt = Smem::RH, SH = Smem::SH, HW = Smem::HW, BW = Smem::BW;
     constexpr int PPT = TY / SEG;                    // centre rows per thread
-    constexpr int HROWS = (RHt + SEG - 1) / SEG;     // h-smoothing rows per thread
     constexpr int BROWS = (SH + SEG - 1) / SEG;      // blend rows per thread
     constexpr int UW = TX + 2, UH = TY + 2, PW = TX + 1, PH = TY + 1;
     static_assert(TY % SEG == 0, "tile height must split into SEG segments");
@@ -130,24 +129,24 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
             fixup(s1t, SH, RW, RW, x0 - 4, y0 - 2);
             __syncthreads();
         }
-        // ---- horizontal smoothing: hs(ry, hx) for image columns x0-2+hx ------------------------
+        // ---- horizontal smoothing: hs(ry, hx) for image columns x0-2+hx; hx sits at raw column hx+2, so
+        //      outputs 4q..4q+3 need raw columns 4q..4q+7: two 16-byte loads feed four outputs --------
         {
+            constexpr int NQ = HW / 4;
+            static_assert(HW % 4 == 0 && RW % 4 == 0 && 4 * (NQ - 1) + 8 <= RW, "quads stay inside a raw row, rows stay 16-byte aligned");
+            for (int task = tid; task < RHt * NQ; task += NT) {
+                const int ry = task / NQ, q = task - ry * NQ;
+                T lo[4], hi[4], out[4];
+                ld4(raw + ry * RW + 4 * q, lo);
+                ld4(raw + ry * RW + 4 * q + 4, hi);
+                const T win[8] = {lo[0], lo[1], lo[2], lo[3], hi[0], hi[1], hi[2], hi[3]};
 #pragma unroll
-            for (int j = 0; j < HROWS; j++) {
-                const int ry = seg * HROWS + j;
-                if (ry < RHt) {
-                    const T* r = raw + ry * RW + col;         // hx = col sits at raw column col+2; r[0] is tap -2
+                for (int j = 0; j < 4; j++) {
                     T acc = 0;
-                    acc += r[0] * g0; acc += r[1] * g1; acc += r[2] * g2; acc += r[3] * g3; acc += r[4] * g4;
-                    sm.hs[ry][col] = acc;
+                    acc += win[j] * g0; acc += win[j + 1] * g1; acc += win[j + 2] * g2; acc += win[j + 3] * g3; acc += win[j + 4] * g4;
+                    out[j] = acc;
                 }
-            }
-            if (tid < 4 * RHt) {                               // columns 64..67
-                const int ry = tid >> 2, hx = TX + (tid & 3);
-                const T* r = raw + ry * RW + hx;
-                T acc = 0;
-                acc += r[0] * g0; acc += r[1] * g1; acc += r[2] * g2; acc += r[3] * g3; acc += r[4] * g4;
-                sm.hs[ry][hx] = acc;
+                st4(&sm.hs[ry][4 * q], out);
             }
         }
         __syncthreads();
