@@ -445,14 +445,34 @@ __device__ __forceinline__ SamplePos sample_pos(int j, float f, int n, float& fr
 #define PF_WARP_PIX 2
 #endif
 constexpr int kWarpPix = PF_WARP_PIX;
+#ifndef PF_WARP_ROWS
+#define PF_WARP_ROWS 1
+#endif
+// launch grid of k_update_warp (128 threads)
+inline dim3 warp_grid(int w, int h) {
+#if PF_WARP_ROWS
+    return dim3((unsigned)((w + 32 * kWarpPix - 1) / (32 * kWarpPix)), (unsigned)((h + 3) / 4));
+#else
+    return dim3((unsigned)((w + 128 * kWarpPix - 1) / (128 * kWarpPix)), (unsigned)h);
+#endif
+}
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
                               T* __restrict__ v, const T* __restrict__ du,
                               const T* __restrict__ dv, int fpitch) {
-    const int W = im1.w, H = im1.h, y = blockIdx.y;
+    // the four warps of a CTA take the same columns of four consecutive rows: their bilinear taps
+    // share image rows (row y+1 of one warp is row y of the next), which L1 then serves
+    const int W = im1.w, H = im1.h;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#if PF_WARP_ROWS
+    const int y = blockIdx.y * 4 + wrp;
+    if (y >= H) return;
+    const int xb = blockIdx.x * (32 * kWarpPix) + lane;   // first pixel of this thread
+#else
+    const int y = blockIdx.y;
     const int xb = (blockIdx.x * (blockDim.x >> 5) + wrp) * (32 * kWarpPix) + lane;   // first pixel of this thread
+#endif
     T uu[kWarpPix], vv[kWarpPix];
 #pragma unroll
     for (int i = 0; i < kWarpPix; i++) {

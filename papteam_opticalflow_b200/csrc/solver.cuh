@@ -657,7 +657,7 @@ class Plan : public PlanBase {
             k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
             std::swap(u_, u2_);
             std::swap(v_, v2_);
-            k_update_warp<T><<<dim3(ceil_div(w, 128 * kWarpPix), h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
+            k_update_warp<T><<<warp_grid(w, h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
             launches_ += 3;
         }
         // Im1 is constant within a level: its smoothed copy is computed once instead of every
@@ -738,7 +738,7 @@ class Plan : public PlanBase {
     void ph_update(int k) {
         Ctx& c = cx_;
         set_phase(PF_T_PHASE6_UPDATE, k);
-        k_update_warp<T><<<dim3(ceil_div(c.w, 128 * kWarpPix), c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
+        k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
         launches_++;
         if (kF64 && lex_) {
             k_noise_accum<T><<<dim3(std::min(8, ceil_div(c.w, 128)), std::min(c.h, 64), fc_), 128, 0, st_>>>(c.f1, c.wf, d_acc_);

@@ -143,7 +143,7 @@ struct Stages {
     static void warpfl(double* out, const double* im1, const double* im2, const double* vx, const double* vy, int h, int w, int c) {
         DevImg<T> a(w, h, c), b(w, h, c), o(w, h, c), u(w, h, 1), v(w, h, 1);
         a.upload(im1); b.upload(im2); u.upload(vx); v.upload(vy);
-        k_update_warp<T><<<dim3(ceil_div(w, 128 * kWarpPix), h), 128>>>(a.img, b.img, o.img, u.img.p, v.img.p, nullptr, nullptr, u.img.pitch);
+        k_update_warp<T><<<warp_grid(w, h), 128>>>(a.img, b.img, o.img, u.img.p, v.img.p, nullptr, nullptr, u.img.pitch);
         PF_CUDA(cudaDeviceSynchronize());
         o.download(out);
     }
