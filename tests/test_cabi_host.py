@@ -75,6 +75,32 @@ def test_no_cpu_fallback_without_gpu():
     out = np.zeros((16, 24, 5))
     rc = L.pf_stage_im2feature(out.ctypes.data_as(_lib.dp), a.ctypes.data_as(_lib.dp), 16, 24, 3, 0, 0, 0)
     assert rc == _lib.PF_ENODEVICE
+    # the sequence / visualisation entry points refuse just as loudly
+    f = np.zeros((16, 24, 3), np.uint8)
+    for output in ("float32", "u16", "bgr8"):
+        with pytest.raises(_lib.PyflowB200Error) as e:
+            pyflow.sequence_flow([f, f, f], devices=[0], output=output)
+        assert e.value.code == _lib.PF_ENODEVICE
+    with pytest.raises(_lib.PyflowB200Error) as e:
+        pyflow.flow_to_bgr(np.zeros((16, 24, 2), np.float32))
+    assert e.value.code == _lib.PF_ENODEVICE
+
+
+def test_sequence_argument_validation_on_the_host():
+    f = np.zeros((16, 24, 3), np.uint8)
+    assert pyflow.sequence_flow([]) == ([], 0.0) and pyflow.sequence_flow([f]) == ([], 0.0)
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f.astype(np.float64)])
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f[:-1]])
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f], output="png")
+    with pytest.raises(ValueError):
+        pyflow.sequence_flow([f, f], outs=[np.zeros((16, 24, 2), np.float64)])
+    with pytest.raises(ValueError):
+        pyflow.flow_to_bgr(np.zeros((16, 24, 3), np.float32))
+    with pytest.raises(ValueError):
+        pyflow.save_flow_u16("/dev/null", np.zeros((4, 4, 3), np.uint16))
 
 
 def test_product_never_references_the_oracle():
