@@ -317,6 +317,10 @@ struct SorStage {
 #ifndef PF_SOR_MINB
 #define PF_SOR_MINB 1
 #endif
+// developer ablation builds (tools/sor_ablation.sh): bit 0 = no sweeps, bit 1 = no write-back, bit 2 = no TMA loads
+#ifndef PF_SORX
+#define PF_SORX 0
+#endif
 template <typename T, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, PF_SOR_MINB)
 k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
@@ -342,6 +346,7 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
     const T one_m = (T)1 - omega;
 
     auto issue = [&](int tile) {
+        if (PF_SORX & 4) return;
         const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;
         mbar_expect_tx(&full_bar, stage_bytes);
@@ -371,17 +376,18 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
         const int rx0 = tx * step_x, ry0 = ty * step_y;   // even by construction
         const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
 
-        mbar_wait(&full_bar, parity);
+        if (!(PF_SORX & 4)) mbar_wait(&full_bar, parity);
         parity ^= 1;
 
         T w[R][2], dxy[R][2], iu[R][2], iv[R][2], bu[R][2], bv[R][2], du[R][2], dv[R][2];
-        T wl[R], wu[2];
+        T wl[R], wr[R], wu[2];   // wl / wr: weights towards the neighbouring lanes' columns, zero at the region edge
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int row = wp * R + r;
             V2 t = *reinterpret_cast<const V2*>(&st.phi[row + 1][2 * lane + 4]);
             w[r][0] = t.x * alpha; w[r][1] = t.y * alpha;
-            wl[r] = st.phi[row + 1][2 * lane + 3] * alpha;
+            wl[r] = lane == 0 ? (T)0 : st.phi[row + 1][2 * lane + 3] * alpha;
+            wr[r] = lane == 31 ? (T)0 : w[r][1];
             t = *reinterpret_cast<const V2*>(&st.pl[0][row][2 * lane]); dxy[r][0] = t.x; dxy[r][1] = t.y;
             t = *reinterpret_cast<const V2*>(&st.pl[1][row][2 * lane]); iu[r][0] = t.x; iu[r][1] = t.y;
             t = *reinterpret_cast<const V2*>(&st.pl[2][row][2 * lane]); iv[r][0] = t.x; iv[r][1] = t.y;
@@ -412,7 +418,41 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
             if (tid == 0 && next < ntiles) issue(next);   // overlaps the sweeps below
         }
 
-        for (int s = 0; s < nsw; s++) {
+        // one pixel of row r (compile-time after unrolling), column p = (r + c) & 1
+        auto update = [&](const int r, const int c, T up_du, T up_dv, T dn_du, T dn_dv) {
+            const int p = (r + c) & 1;
+            // horizontal neighbours: one is the thread's own other column, one lives in the next lane.  The lane at
+            // the region edge gets its own value back from the shuffle and multiplies it by a zero weight.
+            T lw, rw, ldu, ldv, rdu, rdv;
+            if (p == 1) {
+                lw = w[r][0]; ldu = du[r][0]; ldv = dv[r][0];
+                rw = wr[r];
+                rdu = __shfl_down_sync(0xffffffffu, du[r][0], 1);
+                rdv = __shfl_down_sync(0xffffffffu, dv[r][0], 1);
+            } else {
+                lw = wl[r];
+                ldu = __shfl_up_sync(0xffffffffu, du[r][1], 1);
+                ldv = __shfl_up_sync(0xffffffffu, dv[r][1], 1);
+                rw = w[r][0];
+                rdu = du[r][1]; rdv = dv[r][1];
+            }
+            T uw, udu, udv, ddu, ddv;
+            if (r > 0) { uw = w[r - 1][p]; udu = du[r - 1][p]; udv = dv[r - 1][p]; }
+            else       { uw = wu[p];       udu = up_du;        udv = up_dv; }
+            if (r < R - 1) { ddu = du[r + 1][p]; ddv = dv[r + 1][p]; }
+            else           { ddu = dn_du;        ddv = dn_dv; }
+            const T cw = w[r][p];
+            T s1 = bu[r][p] + lw * ldu + rw * rdu + uw * udu + cw * ddu;
+            T s2 = bv[r][p] + lw * ldv + rw * rdv + uw * udv + cw * ddv;
+            s1 -= dxy[r][p] * dv[r][p];
+            T nu = one_m * du[r][p] + iu[r][p] * s1;
+            s2 -= dxy[r][p] * nu;
+            T nv = one_m * dv[r][p] + iv[r][p] * s2;
+            du[r][p] = nu;
+            dv[r][p] = nv;
+        };
+
+        for (int s = 0; s < ((PF_SORX & 1) ? 0 : nsw); s++) {
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const int p_top = c & 1, p_bot = (R - 1 + c) & 1;
@@ -426,39 +466,10 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
                     dn_dv = ex[buf][1][wp + 1][0][2 * lane + p_bot];
                 }
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int p = (r + c) & 1;
-                    T lw, ldu, ldv, rdu, rdv;
-                    if (p == 1) {
-                        lw = w[r][0]; ldu = du[r][0]; ldv = dv[r][0];
-                        rdu = __shfl_down_sync(0xffffffffu, du[r][0], 1);
-                        rdv = __shfl_down_sync(0xffffffffu, dv[r][0], 1);
-                        if (lane == 31) { rdu = 0; rdv = 0; }
-                    } else {
-                        lw = wl[r];
-                        ldu = __shfl_up_sync(0xffffffffu, du[r][1], 1);
-                        ldv = __shfl_up_sync(0xffffffffu, dv[r][1], 1);
-                        if (lane == 0) { ldu = 0; ldv = 0; }
-                        rdu = du[r][1]; rdv = dv[r][1];
-                    }
-                    T uw, udu, udv, ddu, ddv;
-                    if (r > 0) { uw = w[r - 1][p]; udu = du[r - 1][p]; udv = dv[r - 1][p]; }
-                    else       { uw = wu[p];       udu = up_du;        udv = up_dv; }
-                    if (r < R - 1) { ddu = du[r + 1][p]; ddv = dv[r + 1][p]; }
-                    else           { ddu = dn_du;        ddv = dn_dv; }
-                    const T cw = w[r][p];
-                    T s1 = bu[r][p] + lw * ldu + cw * rdu + uw * udu + cw * ddu;
-                    T s2 = bv[r][p] + lw * ldv + cw * rdv + uw * udv + cw * ddv;
-                    s1 -= dxy[r][p] * dv[r][p];
-                    T nu = one_m * du[r][p] + iu[r][p] * s1;
-                    s2 -= dxy[r][p] * nu;
-                    T nv = one_m * dv[r][p] + iv[r][p] * s2;
-                    du[r][p] = nu;
-                    dv[r][p] = nv;
-                }
+                for (int r = 0; r < R; r++) update(r, c, up_du, up_dv, dn_du, dn_dv);
                 buf ^= 1;
                 publish(buf);      // readers of the other buffer are at most one barrier behind
-                __syncthreads();   // (pairwise 64-thread named barriers between neighbouring warps measured 18 % slower)
+                __syncthreads();   // (pairwise 64-thread named barriers and a split-phase mbarrier both measured slower)
             }
         }
 
@@ -476,7 +487,13 @@ k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __
             char* const pu = reinterpret_cast<char*>(du_out) + ((size_t)ya * P + xa) * sizeof(T);
             const ptrdiff_t to_dv = reinterpret_cast<char*>(dv_out) - reinterpret_cast<char*>(du_out);
             const unsigned pitch_b = (unsigned)P * (unsigned)sizeof(T);
-            if (v0 && v1) {
+            if (PF_SORX & 2) {
+                // ablation: keep the values alive without storing them
+                T acc = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) acc += du[r][0] + du[r][1] + dv[r][0] + dv[r][1];
+                if (acc == (T)123456789) du_out[0] = acc;
+            } else if (v0 && v1) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     char* q = pu + (size_t)((unsigned)r * pitch_b);
