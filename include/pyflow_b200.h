@@ -36,6 +36,20 @@ extern "C" {
 #define PF_MODE_FP64_REDBLACK  2 /* FP64 arithmetic, red-black ordering */
 #define PF_MODE_FP32_WAVEFRONT 3 /* FP32 arithmetic, lexicographic ordering */
 
+/* ---- alternative solver branches ----------------------------------------
+ * The reference selects them through two process-global PUBLIC STATIC members,
+ *   OpticalFlow::interpolation {Bilinear, Bicubic}   S/OpticalFlow.h:19-20, default Bilinear S/OpticalFlow.cpp:33
+ *   OpticalFlow::noiseModel    {GMixture, Lap}       S/OpticalFlow.h:21-27, default Lap      S/OpticalFlow.cpp:34
+ * (a user switches them by assigning the statics before the call).  The values below follow the
+ * reference's enum order.  Bicubic: the warp inside the pyramid loop is warpImageBicubicRef, followed
+ * by threshold() inside SmoothFlowSOR (S/OpticalFlow.cpp:517-521, 814-815).  GMixture: the data-term
+ * weight is the two-component Gaussian mixture of S/OpticalFlow.cpp:359-368 / 389-396 with its
+ * parameters re-estimated by three EM steps after every outer iteration (estGaussianMixture, :539-591). */
+#define PF_INTERP_BILINEAR 0
+#define PF_INTERP_BICUBIC  1
+#define PF_NOISE_GMIXTURE  0
+#define PF_NOISE_LAP       1
+
 /* ---- timing report: the reference's timing-map keys (S/OpticalFlow.cpp:850-860), in
  *      milliseconds of GPU time from CUDA events, plus the transfer legs ---------------------- */
 enum {
@@ -63,6 +77,12 @@ const char* pf_version(void);
 int  pf_device_count(void);                       /* number of CUDA devices, 0 if none */
 void* pf_host_alloc(size_t bytes);                /* pinned host memory (NULL on failure) */
 void  pf_host_free(void* p);
+
+/* Process-global solver variant, like the reference's statics (see PF_INTERP_* / PF_NOISE_* above).
+ * It is sampled when a plan is created or a one-shot / batch / sequence call starts; existing plans keep
+ * the variant they were created under, and the plan pool is keyed by it.  Host-only, usable without a GPU. */
+int pf_set_solver_variant(int interpolation, int noise_model);
+int pf_get_solver_variant(int* interpolation, int* noise_model);
 
 /* ---- pyramid geometry: host-only double arithmetic, usable without a GPU --------------------
  * S/GaussianPyramid.cpp:50-53 (level count from minWidth) and :89-106 + S/Image.h:755-756

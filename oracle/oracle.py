@@ -53,12 +53,41 @@ def lib():
         L.oracle_bicubic_warp.argtypes = [_dp] * 5 + [i, i, i]
         L.oracle_coarse2fine_flow.argtypes = [_dp] * 5 + [d, d, i, i, i, i, i, i, i, i, i, i]
         L.oracle_coarse2fine_flow.restype = i
+        L.oracle_set_variant.argtypes = [i, i]
+        L.oracle_set_variant.restype = None
+        L.oracle_gm_get.argtypes = [_dp, _dp, _dp, i]
+        L.oracle_gm_get.restype = None
+        L.oracle_gm_reset.restype = None
+        L.oracle_est_gaussian_mixture.argtypes = [_dp, _dp, i, i, i]
+        L.oracle_est_gaussian_mixture.restype = None
         _lib = L
     return _lib
 
 
 def _c(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def set_variant(interpolation="bilinear", noise_model="lap"):
+    """Process-global switch like the reference's statics OpticalFlow::interpolation / noiseModel
+    (S/OpticalFlow.h:19-27)."""
+    lib().oracle_set_variant({"bilinear": 0, "bicubic": 1}[interpolation], {"gmixture": 0, "lap": 1}[noise_model])
+
+
+def gm_get(c):
+    a = np.zeros(c); s = np.zeros(c); b = np.zeros(c)
+    lib().oracle_gm_get(_p(a), _p(s), _p(b), c)
+    return a, s, b
+
+
+def est_gaussian_mixture(im1, im2, reset=True):
+    """OpticalFlow::estGaussianMixture (S/OpticalFlow.cpp:539-591) from freshly reset parameters."""
+    im1, im2 = _hwc(im1), _hwc(im2)
+    h, w, c = im1.shape
+    if reset:
+        lib().oracle_gm_reset()
+    lib().oracle_est_gaussian_mixture(_p(im1), _p(im2), w, h, c)
+    return gm_get(c)
 
 
 def _p(a):

@@ -296,6 +296,80 @@ void oracle_laplacian(double* out, const double* in, const double* wt, int w, in
     free(flux);
 }
 
+/* --------------------------------------------------------------------------------------------
+ * Alternative solver branches.  The reference selects them through two public
+ * static members, OpticalFlow::interpolation {Bilinear, Bicubic} and OpticalFlow::noiseModel
+ * {GMixture, Lap} (S/OpticalFlow.h:19-27, defaults Bilinear / Lap at S/OpticalFlow.cpp:33-34); the
+ * oracle keeps the same process-global switch.  Enum values follow the reference's declaration order.
+ * ------------------------------------------------------------------------------------------ */
+enum { ORACLE_BILINEAR = 0, ORACLE_BICUBIC = 1 };
+enum { ORACLE_GMIXTURE = 0, ORACLE_LAP = 1 };
+static int g_interp = ORACLE_BILINEAR, g_noise = ORACLE_LAP;
+/* GaussianMixture state, S/NoiseModel.h:17-24 */
+static struct { double alpha[16], sigma[16], beta[16], sigma2[16], beta2[16]; } g_gm;
+
+void oracle_set_variant(int interpolation, int noise_model) { g_interp = interpolation; g_noise = noise_model; }
+
+static void gm_square(void) { /* S/NoiseModel.h:129-136 */
+    for (int i = 0; i < 16; i++) { g_gm.sigma2[i] = g_gm.sigma[i] * g_gm.sigma[i]; g_gm.beta2[i] = g_gm.beta[i] * g_gm.beta[i]; }
+}
+static void gm_reset(void) { /* S/NoiseModel.h:98-108 */
+    for (int i = 0; i < 16; i++) { g_gm.alpha[i] = 0.95; g_gm.sigma[i] = 0.05; g_gm.beta[i] = 0.5; }
+    gm_square();
+}
+/* Quirk: S/NoiseModel.h:10-12 defines PI only #ifndef PI, and S/Image.h:14 has already pulled in
+ * S/Stochastic.h:18-20 by then, so the value the reference's Gaussian() compiles with is 3.1415927. */
+#define ORACLE_PI 3.1415927
+static double gm_gaussian(double x, int i, int k) { /* S/NoiseModel.h:116-122 */
+    if (i == 0) return exp(-x / (2 * g_gm.sigma2[k])) / (2 * ORACLE_PI * g_gm.sigma[k]);
+    return exp(-x / (2 * g_gm.beta2[k])) / (2 * ORACLE_PI * g_gm.beta[k]);
+}
+void oracle_gm_get(double* alpha, double* sigma, double* beta, int c) {
+    for (int k = 0; k < c; k++) { alpha[k] = g_gm.alpha[k]; sigma[k] = g_gm.sigma[k]; beta[k] = g_gm.beta[k]; }
+}
+void oracle_gm_reset(void) { gm_reset(); }
+
+/* Three EM iterations of the two-component mixture on (Im1 - warpIm2)^2 per channel.
+ * S/OpticalFlow.cpp:539-591.  Note the M step starts from para.reset() (:564), i.e. the sums of
+ * sigma and beta start at 0.05 and 0.5, not at zero. */
+void oracle_est_gaussian_mixture(const double* im1, const double* im2, int w, int h, int c) {
+    const double prior = 0.9; /* default argument, S/OpticalFlow.h:44 */
+    size_t n = (size_t)w * h;
+    double* w1 = newz(n * c); double* w2 = newz(n * c);
+    for (int count = 0; count < 3; count++) {
+        double total1[16] = {0}, total2[16] = {0};
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < c; k++) {
+                size_t q = i * c + k;
+                double t = im1[q] - im2[q];
+                t *= t;
+                w1[q] = gm_gaussian(t, 0, k) * g_gm.alpha[k];
+                w2[q] = gm_gaussian(t, 1, k) * (1 - g_gm.alpha[k]);
+                t = w1[q] + w2[q];
+                w1[q] /= t;
+                w2[q] /= t;
+                total1[k] += w1[q];
+                total2[k] += w2[q];
+            }
+        gm_reset();
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < c; k++) {
+                size_t q = i * c + k;
+                double t = im1[q] - im2[q];
+                t *= t;
+                g_gm.sigma[k] += w1[q] * t;
+                g_gm.beta[k] += w2[q] * t;
+            }
+        for (int k = 0; k < c; k++) {
+            g_gm.alpha[k] = total1[k] / (total1[k] + total2[k]) * (1 - prior) + 0.95 * prior;
+            g_gm.sigma[k] = sqrt(g_gm.sigma[k] / total1[k]);
+            g_gm.beta[k] = sqrt(g_gm.beta[k] / total2[k]) * (1 - prior) + 0.3 * prior;
+        }
+        gm_square();
+    }
+    free(w1); free(w2);
+}
+
 /* Per-channel mean |Im1-warpIm2| over elements with 0<d<1e6, 0.001 if none.
  * S/OpticalFlow.cpp:594-639. */
 void oracle_est_laplacian_noise(const double* im1, const double* im2, int w, int h, int c,
@@ -392,7 +466,15 @@ void oracle_assemble(const double* imdx, const double* imdy, const double* imdt,
         for (int k = 0; k < c; k++) {
             size_t q = i * c + k;
             double psi = 0;
-            if (!(lap[k] < 1E-20)) {
+            if (g_noise == ORACLE_GMIXTURE) { /* :362-368, :388-394 */
+                double t = imdt[q] + imdx[q] * du[i] + imdy[q] * dv[i];
+                t *= t;
+                double prob1 = gm_gaussian(t, 0, k) * g_gm.alpha[k];
+                double prob2 = gm_gaussian(t, 1, k) * (1 - g_gm.alpha[k]);
+                double prob11 = prob1 / (2 * g_gm.sigma2[k]);
+                double prob22 = prob2 / (2 * g_gm.beta2[k]);
+                psi = (prob11 + prob22) / (prob1 + prob2);
+            } else if (!(lap[k] < 1E-20)) {
                 double t = imdt[q] + imdx[q] * du[i] + imdy[q] * dv[i];
                 t *= t;
                 psi = 1 / (2 * sqrt(t + eps));
@@ -423,6 +505,9 @@ void oracle_assemble(const double* imdx, const double* imdy, const double* imdt,
  * SmoothFlowSOR.  S/OpticalFlow.cpp:238-536.  u, v, warp are in/out; lap is the persistent
  * LapPara state (c entries used; :530 overwrites it every outer iteration).
  * ------------------------------------------------------------------------------------------ */
+static void bicubic_warp_impl(double* out, const double* ref, const double* im2, const double* vx,
+                              const double* vy, int w, int h, int c, int clamp);
+
 void oracle_smoothflow_sor(const double* f1, const double* f2, double* warp, double* u, double* v,
                            double* lap, int w, int h, int c, double alpha, int n_outer,
                            int n_inner, int n_sor, int order) {
@@ -443,8 +528,10 @@ void oracle_smoothflow_sor(const double* f1, const double* f2, double* warp, dou
             oracle_sor_solve(du, dv, phi, dxy, dx2, dy2, bu, bv, w, h, alpha, 1.8, n_sor, order);
         }
         for (size_t i = 0; i < n; i++) { u[i] += du[i]; v[i] += dv[i]; } /* :513-514 */
-        oracle_warpfl(warp, f1, f2, u, v, w, h, c);                       /* :516 */
-        oracle_est_laplacian_noise(f1, warp, w, h, c, lap);               /* :530 */
+        if (g_interp == ORACLE_BILINEAR) oracle_warpfl(warp, f1, f2, u, v, w, h, c);   /* :515-516 */
+        else bicubic_warp_impl(warp, f1, f2, u, v, w, h, c, 1);           /* :517-521 warpImageBicubicRef + threshold */
+        if (g_noise == ORACLE_GMIXTURE) oracle_est_gaussian_mixture(f1, warp, w, h, c); /* :524-527 */
+        else oracle_est_laplacian_noise(f1, warp, w, h, c, lap);          /* :528-530 */
     }
     free(imdx); free(imdy); free(imdt); free(du); free(dv);
     free(phi); free(dxy); free(dx2); free(dy2); free(bu); free(bv);
@@ -490,8 +577,8 @@ static const bicubic_row BICUBIC[4][4] = {
           {4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1}}},
 };
 
-void oracle_bicubic_warp(double* out, const double* ref, const double* im2, const double* vx,
-                         const double* vy, int w, int h, int c) {
+static void bicubic_warp_impl(double* out, const double* ref, const double* im2, const double* vx,
+                              const double* vy, int w, int h, int c, int clamp) {
     static const double d3[3] = {-0.5, 0, 0.5};
     size_t n = (size_t)w * h * c;
     double* ix = newz(n); double* iy = newz(n); double* ixy = newz(n);
@@ -527,17 +614,21 @@ void oracle_bicubic_warp(double* out, const double* ref, const double* im2, cons
                              a[1][0] * dx + a[1][1] * dx * dy + a[1][2] * dx * dy2 + a[1][3] * dx * dy3 +
                              a[2][0] * dx2 + a[2][1] * dx2 * dy + a[2][2] * dx2 * dy2 + a[2][3] * dx2 * dy3 +
                              a[3][0] * dx3 + a[3][1] * dx3 * dy + a[3][2] * dx3 * dy2 + a[3][3] * dx3 * dy3;
-                if (val < 0) val = 0; /* threshold(): clamp to [0,1] for floating images */
-                if (val > 1) val = 1;
                 out[p * c + k] = val;
             }
         }
-    /* the fallback copies of Im1 are clamped by threshold() as well */
-    for (size_t i = 0; i < n; i++) {
-        if (out[i] < 0) out[i] = 0;
-        if (out[i] > 1) out[i] = 1;
-    }
+    /* threshold(): clamp to [0,1] for floating images; the fallback copies of Im1 are clamped as well */
+    if (clamp)
+        for (size_t i = 0; i < n; i++) {
+            if (out[i] < 0) out[i] = 0;
+            if (out[i] > 1) out[i] = 1;
+        }
     free(ix); free(iy); free(ixy);
+}
+
+void oracle_bicubic_warp(double* out, const double* ref, const double* im2, const double* vx,
+                         const double* vy, int w, int h, int c) {
+    bicubic_warp_impl(out, ref, im2, vx, vy, w, h, c, 1);
 }
 
 /* Flow file encoding.
@@ -584,6 +675,7 @@ int oracle_coarse2fine_flow(double* vx, double* vy, double* warp_out, const doub
     int fc = (c == 1) ? 3 : (c == 3 ? 5 : c);
     double lap[16];
     for (int k = 0; k < 16; k++) lap[k] = 0.02; /* :773-775 */
+    if (g_noise == ORACLE_GMIXTURE) gm_reset();  /* :769-770 */
     /* NB: the driver divides the flow by the ORIGINAL ratio argument (:810), while the pyramid
      * silently substitutes 0.75 for out-of-range ratios; the fork always passes 0.75. */
     size_t n0 = (size_t)w * h;
@@ -605,7 +697,8 @@ int oracle_coarse2fine_flow(double* vx, double* vy, double* warp_out, const doub
             memcpy(u, t, sizeof(double) * ln);
             oracle_resize_to(v, t, pw, ph, 1, lw, lh, 1 / ratio);
             memcpy(v, t, sizeof(double) * ln);
-            oracle_warpfl(wf, f1, f2, u, v, lw, lh, fc);
+            if (g_interp == ORACLE_BILINEAR) oracle_warpfl(wf, f1, f2, u, v, lw, lh, fc); /* :812-813 */
+            else bicubic_warp_impl(wf, f1, f2, u, v, lw, lh, fc, 0); /* :814-815: no threshold() here */
         }
         oracle_smoothflow_sor(f1, f2, wf, u, v, lap, lw, lh, fc, alpha, n_outer + k, n_inner,
                               n_sor + k * 3, order);

@@ -55,6 +55,10 @@ class _Ref:
         L.ref_stage_pyramid.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                         C.c_int, _ip, _ip, _dp]
         L.ref_stage_pyramid.restype = C.c_int
+        L.ref_set_variant.argtypes = [C.c_int, C.c_int]
+        L.ref_set_variant.restype = None
+        L.ref_gm_get.argtypes = [_dp, _dp, _dp, C.c_int]
+        L.ref_gm_get.restype = None
         if not parallel:
             L.ref_coarse2fine_flow.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double,
                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -76,6 +80,16 @@ class _Ref:
             L.ref_stage_smoothflow_sor.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
                                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                    C.c_int]
+
+    # -- alternative solver branches: the reference's public statics ------
+    def set_variant(self, interpolation="bilinear", noise_model="lap"):
+        """OpticalFlow::interpolation / OpticalFlow::noiseModel (S/OpticalFlow.h:19-27)."""
+        self.lib.ref_set_variant({"bilinear": 0, "bicubic": 1}[interpolation], {"gmixture": 0, "lap": 1}[noise_model])
+
+    def gm_get(self, c):
+        a = np.zeros(c); s = np.zeros(c); b = np.zeros(c)
+        self.lib.ref_gm_get(_p(a), _p(s), _p(b), c)
+        return a, s, b
 
     # -- the fork's entry point (pyramidLevels, nCores) ---------------------------------------
     def coarse2fine_flow_levels(self, im1, im2, levels, ncores=1):

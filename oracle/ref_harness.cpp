@@ -50,15 +50,39 @@ void smooth_flow_sor(const DImage& I1, const DImage& I2, DImage& warp, DImage& u
 #endif
 }
 
-void init_lap(int image_channels) {
-    // S/OpticalFlow.cpp:773-775
-    OpticalFlow::LapPara.allocate(image_channels + 2);
-    for (int i = 0; i < OpticalFlow::LapPara.dim(); i++) OpticalFlow::LapPara[i] = 0.02;
+void init_noise(int image_channels) {
+    // S/OpticalFlow.cpp:768-776
+    switch (OpticalFlow::noiseModel) {
+        case OpticalFlow::GMixture:
+            OpticalFlow::GMPara.reset(image_channels + 2);
+            break;
+        case OpticalFlow::Lap:
+            OpticalFlow::LapPara.allocate(image_channels + 2);
+            for (int i = 0; i < OpticalFlow::LapPara.dim(); i++) OpticalFlow::LapPara[i] = 0.02;
+            break;
+    }
 }
 
 }  // namespace
 
 extern "C" {
+
+// The alternative solver branches are selected in the reference by two PUBLIC
+// static members (S/OpticalFlow.h:19-27; defaults Bilinear / Lap at S/OpticalFlow.cpp:33-34): the harness
+// assigns them, the reference's sources stay untouched.  interpolation: 0 Bilinear, 1 Bicubic;
+// noise_model: 0 GMixture, 1 Lap (the reference's enum order).
+void ref_set_variant(int interpolation, int noise_model) {
+    OpticalFlow::interpolation = interpolation ? OpticalFlow::Bicubic : OpticalFlow::Bilinear;
+    OpticalFlow::noiseModel = noise_model ? OpticalFlow::Lap : OpticalFlow::GMixture;
+}
+// current mixture parameters (after a solve: the state left by the last estGaussianMixture call)
+void ref_gm_get(double* alpha, double* sigma, double* beta, int c) {
+    for (int k = 0; k < c && k < OpticalFlow::GMPara.nChannels; k++) {
+        alpha[k] = OpticalFlow::GMPara.alpha[k];
+        sigma[k] = OpticalFlow::GMPara.sigma[k];
+        beta[k] = OpticalFlow::GMPara.beta[k];
+    }
+}
 
 // Fills `timing_out` (if non-NULL, capacity `cap`) with "key=value\n" lines of the timing map.
 int ref_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const double* Im1,
@@ -121,7 +145,7 @@ int ref_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* I
     P2.ConstructPyramid(I2, ratio, minWidth);
     // NB: ConstructPyramid substitutes 0.75 for an out-of-range ratio only in its local copy; the
     // upstream driver keeps dividing the flow by the caller's ratio, and so does this harness.
-    init_lap(I1.nchannels());
+    init_noise(I1.nchannels());
     DImage F1, F2, WF;
     for (int k = P1.nlevels() - 1; k >= 0; k--) {
         int lw = P1.Image(k).width(), lh = P1.Image(k).height();
@@ -136,7 +160,8 @@ int ref_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* I
             VX.Multiplywith(1 / ratio);
             VY.imresize(lw, lh);
             VY.Multiplywith(1 / ratio);
-            OpticalFlow::warpFL(WF, F1, F2, VX, VY);
+            if (OpticalFlow::interpolation == OpticalFlow::Bilinear) OpticalFlow::warpFL(WF, F1, F2, VX, VY);
+            else F2.warpImageBicubicRef(F1, WF, VX, VY);   // S/OpticalFlow.cpp:812-815
         }
         smooth_flow_sor(F1, F2, WF, VX, VY, alpha, nOuter + k, nInner, nSOR + k * 3);
     }
@@ -228,7 +253,7 @@ void ref_stage_smoothflow_sor(const double* f1, const double* f2, double* warp, 
     load(Wp, warp, h, w, c);
     load(U, u, h, w, 1);
     load(V, v, h, w, 1);
-    if (lap_init_channels > 0) init_lap(lap_init_channels);
+    if (lap_init_channels > 0) init_noise(lap_init_channels);
     smooth_flow_sor(A, B, Wp, U, V, alpha, nOuter, nInner, nSOR);
     store(warp, Wp);
     store(u, U);

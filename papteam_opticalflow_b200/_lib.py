@@ -48,6 +48,8 @@ def lib():
         "pf_coarse2fine_flow": (i, [dp, dp, dp, dp, dp, d, d, i, i, i, i, i, i, i, i, i, i, dp]),
         "pf_coarse2fine_flow_levels": (i, [dp, dp, dp, dp, dp, i, i, i, i, i, i, i, dp]),
         "pf_pool_clear": (i, []),
+        "pf_set_solver_variant": (i, [i, i]),
+        "pf_get_solver_variant": (i, [ip, ip]),
         "pf_plan_create": (i, [C.POINTER(v), i, i, i, d, d, i, i, i, i, i, i, i, i]),
         "pf_plan_destroy": (i, [v]),
         "pf_plan_levels": (i, [v]),

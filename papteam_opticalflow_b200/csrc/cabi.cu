@@ -89,11 +89,7 @@ std::vector<PoolEntry> g_pool;
 unsigned long long g_pool_clock = 0;
 const size_t kPoolMax = 16;
 
-bool same_params(const Params& a, const Params& b) {
-    return a.h == b.h && a.w == b.w && a.c == b.c && a.alpha == b.alpha && a.ratio == b.ratio &&
-           a.min_width == b.min_width && a.levels == b.levels && a.n_outer == b.n_outer && a.n_inner == b.n_inner &&
-           a.n_sor == b.n_sor && a.col_type == b.col_type && a.mode == b.mode && a.device == b.device;
-}
+bool same_params(const Params& a, const Params& b) { return same_solver(a, b) && a.device == b.device; }
 
 void pool_release(pf_plan* pl) {
     std::lock_guard<std::mutex> g(g_pool_mu);
@@ -176,6 +172,22 @@ void* pf_host_alloc(size_t bytes) {
 }
 void pf_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int pf_set_solver_variant(int interpolation, int noise_model) {
+    if (interpolation != PF_INTERP_BILINEAR && interpolation != PF_INTERP_BICUBIC)
+        return fail(PF_EINVAL, "interpolation must be PF_INTERP_BILINEAR or PF_INTERP_BICUBIC");
+    if (noise_model != PF_NOISE_GMIXTURE && noise_model != PF_NOISE_LAP)
+        return fail(PF_EINVAL, "noise_model must be PF_NOISE_GMIXTURE or PF_NOISE_LAP");
+    solver_variant().interp = interpolation;
+    solver_variant().noise = noise_model;
+    return PF_OK;
+}
+
+int pf_get_solver_variant(int* interpolation, int* noise_model) {
+    if (interpolation) *interpolation = solver_variant().interp;
+    if (noise_model) *noise_model = solver_variant().noise;
+    return PF_OK;
 }
 
 int pf_pyramid_levels(int width, double ratio, int minWidth) {

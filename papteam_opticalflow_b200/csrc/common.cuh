@@ -59,6 +59,19 @@ struct Taps {
 };
 
 // solver parameters after the boundary has normalised both call shapes
+// Alternative solver branches.  In the reference they are two process-global public
+// statics, OpticalFlow::interpolation / OpticalFlow::noiseModel (S/OpticalFlow.h:19-27, defaults Bilinear / Lap
+// at S/OpticalFlow.cpp:33-34); here the same process-global switch (pf_set_solver_variant) is sampled whenever
+// solver parameters are put together, so a plan keeps the variant it was created under.
+struct SolverVariant {
+    int interp = PF_INTERP_BILINEAR;
+    int noise = PF_NOISE_LAP;
+};
+inline SolverVariant& solver_variant() {
+    static SolverVariant v;
+    return v;
+}
+
 struct Params {
     int h, w, c;
     double alpha, ratio;
@@ -66,7 +79,14 @@ struct Params {
     int n_outer, n_inner, n_sor;
     int col_type;
     int mode, device;
+    int interp = solver_variant().interp;   // PF_INTERP_*: warp inside the pyramid loop
+    int noise = solver_variant().noise;     // PF_NOISE_*: data-term weight model
 };
+inline bool same_solver(const Params& a, const Params& b) {
+    return a.h == b.h && a.w == b.w && a.c == b.c && a.alpha == b.alpha && a.ratio == b.ratio && a.min_width == b.min_width &&
+           a.levels == b.levels && a.n_outer == b.n_outer && a.n_inner == b.n_inner && a.n_sor == b.n_sor &&
+           a.col_type == b.col_type && a.mode == b.mode && a.interp == b.interp && a.noise == b.noise;
+}
 
 inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }
 inline bool mode_is_lex(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP32_WAVEFRONT; }

@@ -719,21 +719,35 @@ struct BicubicTable {
     signed char wt[16][16];
 };
 
+// Destination of the bicubic warp: the boundary's HWC float64 buffer (final im2W, always clamped:
+// S/OpticalFlow.cpp:841-842) or a planar image of the solver (the Bicubic inner warp of
+// S/OpticalFlow.cpp:517-521 with threshold(), and the level-start warp of :814-815 without it).
+template <typename T>
+struct BicubicOut {
+    double* hwc;      // non-null: HWC float64, clamped
+    Img<T> planar;    // used when hwc == nullptr
+    int clamp;        // planar output only
+    __device__ __forceinline__ void put(int x, int y, int w, int C, int k, T val) const {
+        if (hwc) {
+            hwc[((size_t)y * w + x) * C + k] = (double)min(max(val, (T)0), (T)1);
+        } else {
+            if (clamp) val = min(max(val, (T)0), (T)1);
+            planar.ch(k)[(size_t)y * planar.pitch + x] = val;
+        }
+    }
+};
+
 template <typename T>
 __global__ void k_bicubic_warp(Img<T> ref, Img<T> im, Img<T> ix, Img<T> iy, Img<T> ixy,
                                const T* __restrict__ u, const T* __restrict__ v, int fpitch,
-                               const BicubicTable* __restrict__ tab, double* __restrict__ out) {
+                               const BicubicTable* __restrict__ tab, BicubicOut<T> out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= im.w) return;
     int w = im.w, h = im.h, C = im.c;
     size_t of = (size_t)y * fpitch + x;
     double sx = (double)x + (double)u[of], sy = (double)y + (double)v[of];
-    double* o = out + ((size_t)y * w + x) * C;
     if (sx < 0 || sx > w - 1 || sy < 0 || sy > h - 1) {
-        for (int k = 0; k < C; k++) {
-            T r = ref.ch(k)[(size_t)y * ref.pitch + x];
-            o[k] = (double)min(max(r, (T)0), (T)1);
-        }
+        for (int k = 0; k < C; k++) out.put(x, y, w, C, k, ref.ch(k)[(size_t)y * ref.pitch + x]);
         return;
     }
     int x0 = clampi((int)sx, w), x1 = clampi((int)sx + 1, w);
@@ -764,7 +778,7 @@ __global__ void k_bicubic_warp(Img<T> ref, Img<T> im, Img<T> ix, Img<T> iy, Img<
                 val += py[corner[t]] * by[t];
                 val += pz[corner[t]] * bz[t];
             }
-            o[k] = (double)min(max(val, (T)0), (T)1);
+            out.put(x, y, w, C, k, val);
         }
         return;
     }
@@ -785,8 +799,19 @@ __global__ void k_bicubic_warp(Img<T> ref, Img<T> im, Img<T> ix, Img<T> iy, Img<
                 a[4] * dx + a[5] * dx * dy + a[6] * dx * dy2 + a[7] * dx * dy3 +
                 a[8] * dx2 + a[9] * dx2 * dy + a[10] * dx2 * dy2 + a[11] * dx2 * dy3 +
                 a[12] * dx3 + a[13] * dx3 * dy + a[14] * dx3 * dy2 + a[15] * dx3 * dy3;
-        o[k] = (double)min(max(val, (T)0), (T)1);
+        out.put(x, y, w, C, k, val);
     }
+}
+
+// u += du, v += dv (S/OpticalFlow.cpp:513-514) on its own: the Bicubic inner warp does not go through k_update_warp
+template <typename T>
+__global__ void k_add_flow(T* __restrict__ u, T* __restrict__ v, const T* __restrict__ du, const T* __restrict__ dv,
+                           int w, int pitch) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    size_t o = (size_t)y * pitch + x;
+    u[o] += du[o];
+    v[o] += dv[o];
 }
 
 // Host-side definition of the table (shared by both instantiations).

@@ -65,9 +65,7 @@ class MultiPlan {
         if ((int)devs_.size() != ndev || split_min != split_min_) return false;
         for (int g = 0; g < ndev; g++)
             if (devs_[g] != devices[g]) return false;
-        return P.h == p.h && P.w == p.w && P.c == p.c && P.alpha == p.alpha && P.ratio == p.ratio && P.min_width == p.min_width &&
-               P.levels == p.levels && P.n_outer == p.n_outer && P.n_inner == p.n_inner && P.n_sor == p.n_sor &&
-               P.col_type == p.col_type && P.mode == p.mode;
+        return same_solver(P, p);
     }
 
     // returns milliseconds of the solve (host clock around device-synchronised region)

@@ -269,6 +269,8 @@ class Plan : public PlanBase {
             if (g.w < 1 || g.h < 1) throw Error(PF_EINVAL, "pyramid level collapsed to zero size");
         fc_ = P.c == 1 ? 3 : (P.c == 3 ? 5 : P.c);
         if (fc_ > 16) throw Error(PF_EUNSUPPORTED, "more than 16 channels");
+        bicubic_ = P.interp == PF_INTERP_BICUBIC;
+        gmix_ = P.noise == PF_NOISE_GMIXTURE;
         const char* e = getenv("PF_NO_GRAPH");
         use_graph_ = !(e && atoi(e)) && !lex_;
         e = getenv("PF_UNFUSED");
@@ -437,6 +439,7 @@ class Plan : public PlanBase {
         total += 3 * Arena::need(pl0 * P.c, sizeof(T));                  // bicubic ix, iy, ixy
         total += 10 * Arena::need(pl0 * fc_, sizeof(T));                 // f1 f2 wf s1 s2 tmp blend dx dy dt
         total += 16 * Arena::need(pl0, sizeof(T));                       // scalar planes
+        if (bicubic_) total += 3 * Arena::need(pl0 * fc_, sizeof(T));    // gradients of the Im2 features (Bicubic inner warp)
         total += Arena::need(64, sizeof(double)) * 3 + Arena::need(1, sizeof(BicubicTable));
         arena_.reserve(total + 4096);
         d_in1_ = arena_.take<double>(in_elems);
@@ -460,6 +463,11 @@ class Plan : public PlanBase {
         for (T** b : fcb) *b = arena_.take<T>(pl0 * fc_);
         T** sc[] = {&u_, &v_, &u2_, &v2_, &du_, &dv_, &du2_, &dv2_, &phi_, &dxy_, &iu_, &iv_, &bu_, &bv_, &dx2_, &dy2_};
         for (T** b : sc) *b = arena_.take<T>(pl0);
+        if (bicubic_) {
+            g_ix_ = arena_.take<T>(pl0 * fc_);
+            g_iy_ = arena_.take<T>(pl0 * fc_);
+            g_ixy_ = arena_.take<T>(pl0 * fc_);
+        }
         d_lap_ = arena_.take<double>(64);
         d_acc_ = arena_.take<double>(64);
         d_tab_ = arena_.take<BicubicTable>(1);
@@ -563,6 +571,7 @@ class Plan : public PlanBase {
         int pw, ph;                                                   // previous (coarser) level size
         int w, h, pitch;                                              // current level
         Img<T> f1, f2, wf, s1, s2, tmp, blend, imdx, imdy, imdt;
+        Img<T> gix, giy, gixy;                                        // Bicubic inner warp: derivative images of f2
         FusedMaps fmaps;
     };
     Ctx cx_;
@@ -643,6 +652,16 @@ class Plan : public PlanBase {
             k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr2_[k], c.f2);
         }
         launches_ += 2;
+        if (bicubic_) {
+            // warpImageBicubicRef differentiates the image it warps on every call (S/Image.h:2587-2595); the
+            // Im2 features are constant within a level, so the three derivative images are computed once
+            const double one[1] = {1.0};
+            const Taps<T> id = make_taps<T>(one, 0);
+            c.gix = view(g_ix_, w, h, fc_); c.giy = view(g_iy_, w, h, fc_); c.gixy = view(g_ixy_, w, h, fc_);
+            filter_hv(c.f2, c.gix, c.d3, id);
+            filter_hv(c.f2, c.giy, id, c.d3);
+            filter_hv(c.f2, c.gixy, c.d3, c.d3);
+        }
         if (k == nlev_ - 1) {
             PF_CUDA(cudaMemsetAsync(u_, 0, plane_bytes, st_));
             PF_CUDA(cudaMemsetAsync(v_, 0, plane_bytes, st_));
@@ -657,8 +676,13 @@ class Plan : public PlanBase {
             k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
             std::swap(u_, u2_);
             std::swap(v_, v2_);
-            k_update_warp<T><<<warp_grid(w, h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
-            launches_ += 3;
+            launches_ += 2;
+            if (bicubic_) {
+                bicubic_inner(k, 0);   // S/OpticalFlow.cpp:814-815: no threshold() at the level start
+            } else {
+                k_update_warp<T><<<warp_grid(w, h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
+                launches_++;
+            }
         }
         // Im1 is constant within a level: its smoothed copy is computed once instead of every
         // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
@@ -728,6 +752,16 @@ class Plan : public PlanBase {
         }
     }
 
+    // Bicubic warp of the Im2 features into the warped-feature image of this level (interpolation == Bicubic)
+    void bicubic_inner(int k, int clamp) {
+        (void)k;
+        Ctx& c = cx_;
+        BicubicOut<T> bo;
+        bo.hwc = nullptr; bo.planar = c.wf; bo.clamp = clamp;
+        k_bicubic_warp<T><<<grid2(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.gix, c.giy, c.gixy, u_, v_, c.pitch, d_tab_, bo);
+        launches_++;
+    }
+
     // -- Phase5: SOR on this device alone --
     void ph_sor(int k) {
         set_phase(PF_T_PHASE5_SOR, k);
@@ -738,8 +772,14 @@ class Plan : public PlanBase {
     void ph_update(int k) {
         Ctx& c = cx_;
         set_phase(PF_T_PHASE6_UPDATE, k);
-        k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
-        launches_++;
+        if (bicubic_) {
+            k_add_flow<T><<<grid2(c.w, c.h), 128, 0, st_>>>(u_, v_, du_, dv_, c.w, c.pitch);
+            launches_++;
+            bicubic_inner(k, 1);   // S/OpticalFlow.cpp:517-521: warpImageBicubicRef + threshold()
+        } else {
+            k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
+            launches_++;
+        }
         if (kF64 && lex_) {
             k_noise_accum<T><<<dim3(std::min(8, ceil_div(c.w, 128)), std::min(c.h, 64), fc_), 128, 0, st_>>>(c.f1, c.wf, d_acc_);
             k_noise_final<<<1, 32, 0, st_>>>(d_acc_, d_lap_, fc_);
@@ -759,7 +799,9 @@ class Plan : public PlanBase {
         filter_hv(im2, ix, c.d3, id);
         filter_hv(im2, iy, id, c.d3);
         filter_hv(im2, ixy, c.d3, c.d3);
-        k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, d_warp_);
+        BicubicOut<T> bo;
+        bo.hwc = d_warp_; bo.clamp = 1;
+        k_bicubic_warp<T><<<grid2(P.w, P.h), 128, 0, st_>>>(im1, im2, ix, iy, ixy, u_, v_, pitch_for(P.w), d_tab_, bo);
         Img<T> uo = view(u_, P.w, P.h, 1), vo = view(v_, P.w, P.h, 1);
         k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(uo, d_vx_);
         k_export_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(vo, d_vy_);
@@ -893,6 +935,7 @@ class Plan : public PlanBase {
 #endif
     static constexpr int kFTX = 64, kFTY = kF64 ? 16 : PF_FUSED_TY, kFSEG = kF64 ? 8 : PF_FUSED_SEG;   // k_fused_* tile, 64*SEG threads
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
+    bool bicubic_ = false, gmix_ = false;   // alternative solver branches
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;
     std::vector<Level> geo_;
@@ -912,6 +955,7 @@ class Plan : public PlanBase {
     double *d_in1_ = nullptr, *d_in2_ = nullptr, *d_warp_ = nullptr, *d_vx_ = nullptr, *d_vy_ = nullptr;
     std::vector<Img<T>> pyr1_, pyr2_;
     T *b_tmp_ = nullptr, *b_out_ = nullptr, *b_ix_ = nullptr, *b_iy_ = nullptr, *b_ixy_ = nullptr;
+    T *g_ix_ = nullptr, *g_iy_ = nullptr, *g_ixy_ = nullptr;
     T *f1_ = nullptr, *f2_ = nullptr, *wf_ = nullptr, *s1_ = nullptr, *s2_ = nullptr, *tmp_ = nullptr;
     T *blend_ = nullptr, *imdx_ = nullptr, *imdy_ = nullptr, *imdt_ = nullptr;
     T *u_ = nullptr, *v_ = nullptr, *u2_ = nullptr, *v2_ = nullptr, *du_ = nullptr, *dv_ = nullptr;

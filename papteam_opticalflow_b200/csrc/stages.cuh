@@ -168,7 +168,9 @@ struct Stages {
         k_filter_h<T><<<g2(w, h, c), 128>>>(b.img, ix.img, d3());
         k_filter_v<T><<<g2(w, h, c), 128>>>(b.img, iy.img, d3());
         k_filter_v<T><<<g2(w, h, c), 128>>>(ix.img, ixy.img, d3());
-        k_bicubic_warp<T><<<g2(w, h), 128>>>(r.img, b.img, ix.img, iy.img, ixy.img, u.img.p, v.img.p, u.img.pitch, dtab, dout);
+        BicubicOut<T> bo;
+        bo.hwc = dout; bo.clamp = 1;
+        k_bicubic_warp<T><<<g2(w, h), 128>>>(r.img, b.img, ix.img, iy.img, ixy.img, u.img.p, v.img.p, u.img.pitch, dtab, bo);
         cudaError_t e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);
         cudaFree(dtab);
         cudaFree(dout);

@@ -33,6 +33,29 @@ _TIMING_KEYS = ["Total C++ Execution", "Construction", "Allocation", "Phase1_Gen
                 "Phase6_Update", "PostProcessing", "H2D", "D2H", "Solve"]
 
 
+INTERPOLATIONS = {"bilinear": 0, "bicubic": 1}
+NOISE_MODELS = {"gmixture": 0, "lap": 1}
+
+
+def set_solver_variant(interpolation="bilinear", noise_model="lap"):
+    """Selects the alternative solver branches the reference keeps behind two process-global public statics,
+    `OpticalFlow::interpolation` and `OpticalFlow::noiseModel` (S/OpticalFlow.h:19-27; defaults Bilinear / Lap at
+    S/OpticalFlow.cpp:33-34).  Like there, the switch is process-global; it is sampled when a plan is created or a
+    one-shot / batch / sequence call starts."""
+    if interpolation not in INTERPOLATIONS:
+        raise ValueError("unknown interpolation %r (expected one of %s)" % (interpolation, sorted(INTERPOLATIONS)))
+    if noise_model not in NOISE_MODELS:
+        raise ValueError("unknown noise_model %r (expected one of %s)" % (noise_model, sorted(NOISE_MODELS)))
+    check(_lib.lib().pf_set_solver_variant(INTERPOLATIONS[interpolation], NOISE_MODELS[noise_model]))
+
+
+def get_solver_variant():
+    a, b = C.c_int(), C.c_int()
+    check(_lib.lib().pf_get_solver_variant(C.byref(a), C.byref(b)))
+    inv = lambda d, v: [k for k, x in d.items() if x == v][0]
+    return inv(INTERPOLATIONS, a.value), inv(NOISE_MODELS, b.value)
+
+
 def _mode_id(mode):
     if mode is None:
         mode = os.environ.get("PYFLOW_B200_MODE", "fp32_redblack")
@@ -200,7 +223,7 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
         raise ValueError("Im1 and Im2 must have the same shape, got %s and %s" % (Im1.shape, Im2.shape))
     h, w, c = Im1.shape
     mid = _mode_id(mode)
-    key = (h, w, c, tuple(sorted(p.items())), levels, mid, int(device))
+    key = (h, w, c, tuple(sorted(p.items())), levels, mid, int(device), get_solver_variant())
     plan = _get_plan(key, h=h, w=w, c=c, levels=levels, mode=mid, device=device, **p)
     t, vx, vy, wi = plan.execute(Im1, Im2)
     if fork:

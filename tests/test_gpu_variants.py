@@ -1,0 +1,74 @@
+"""GPU parity of the alternative solver branches through the drop-in module, against the golden
+vectors recorded from the unmodified reference with its public statics assigned (tests/golden/make_golden_variants.py).
+Parity mode: max |flow difference| <= 1e-6; fast mode: mean EPE <= 0.02 px, max <= 0.5 px."""
+import numpy as np
+import pytest
+
+import pyflow
+from conftest import golden, load_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def crop():
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    return np.ascontiguousarray(a[:96, :128]), np.ascontiguousarray(b[:96, :128])
+
+
+@pytest.fixture()
+def variant():
+    yield pyflow.set_solver_variant
+    pyflow.set_solver_variant("bilinear", "lap")
+
+
+def epe(u, v, gu, gv):
+    return np.hypot(u - gu, v - gv)
+
+
+def test_bicubic_inner_warp_parity_mode(variant):
+    g = golden("variants_128x96.npz")
+    a, b = crop()
+    variant("bicubic", "lap")
+    assert pyflow.get_solver_variant() == ("bicubic", "lap")
+    _, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 4, 1, mode="fp64_wavefront")
+    assert np.abs(vx - g["bicubic_fork_vx"]).max() <= 1e-6 and np.abs(vy - g["bicubic_fork_vy"]).max() <= 1e-6
+    assert np.abs(wi - g["bicubic_fork_warp"]).max() <= 1e-6
+    u, v, w2 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 5, 1, 20, 0, mode="fp64_wavefront")
+    assert np.abs(u - g["bicubic_up_vx"]).max() <= 1e-6 and np.abs(v - g["bicubic_up_vy"]).max() <= 1e-6
+    assert np.abs(w2 - g["bicubic_up_warp"]).max() <= 1e-6
+    ag, bg = np.ascontiguousarray(a.mean(axis=2, keepdims=True)), np.ascontiguousarray(b.mean(axis=2, keepdims=True))
+    u, v, w2 = pyflow.coarse2fine_flow(ag, bg, 0.012, 0.75, 20, 4, 2, 15, 1, mode="fp64_wavefront")
+    assert np.abs(u - g["bicubic_gray_vx"]).max() <= 1e-6 and np.abs(v - g["bicubic_gray_vy"]).max() <= 1e-6
+    assert np.abs(w2 - g["bicubic_gray_warp"]).max() <= 1e-6
+
+
+def test_bicubic_inner_warp_fast_mode_and_variant_isolation(variant):
+    g = golden("variants_128x96.npz")
+    a, b = crop()
+    variant("bicubic", "lap")
+    _, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 4, 1, mode="fp32_redblack")
+    e = epe(vx, vy, g["bicubic_fork_vx"], g["bicubic_fork_vy"])
+    assert e.mean() <= 0.02 and e.max() <= 0.5, (e.mean(), e.max())
+    assert np.abs(wi - g["bicubic_fork_warp"]).mean() <= 1e-3
+    # plans are cached and pooled per variant: switching back gives the default (bilinear) solver again, and it differs
+    variant("bilinear", "lap")
+    _, bx, by, _ = pyflow.coarse2fine_flow(a, b, 4, 1, mode="fp32_redblack")
+    assert np.abs(bx - vx).max() > 1e-3
+    variant("bicubic", "lap")
+    _, cx, cy, _ = pyflow.coarse2fine_flow(a, b, 4, 1, mode="fp32_redblack")
+    assert np.array_equal(cx, vx) and np.array_equal(cy, vy)
+
+
+def test_bicubic_inner_warp_vs_oracle_at_240(variant, oracle_mod):
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    try:
+        oracle_mod.set_variant("bicubic", "lap")
+        ox, oy, ow = oracle_mod.coarse2fine_flow(a, b, levels=8)
+    finally:
+        oracle_mod.set_variant("bilinear", "lap")
+    variant("bicubic", "lap")
+    _, vx, vy, wi = pyflow.coarse2fine_flow(a, b, 8, 1, mode="fp64_wavefront")
+    assert max(np.abs(vx - ox).max(), np.abs(vy - oy).max()) <= 1e-6 and np.abs(wi - ow).max() <= 1e-6
+    _, fx, fy, _ = pyflow.coarse2fine_flow(a, b, 8, 1, mode="fp32_redblack")
+    e = epe(fx, fy, ox, oy)
+    assert e.mean() <= 0.02 and e.max() <= 0.5, (e.mean(), e.max())
