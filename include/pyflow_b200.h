@@ -136,6 +136,10 @@ int pf_multi_solve(pf_plan* const* plans, int nplans, int repeats, double* ms_to
 /* Per-level phase times (ms) of the last pf_plan_profile call: out[level][PF_NUM_TIMINGS];
  * returns the number of levels written. */
 int pf_plan_level_timings(const pf_plan* plan, double* out, int max_levels);
+/* Gaussian-mixture parameters (alpha, sigma, beta per feature channel) a PF_NOISE_GMIXTURE plan holds after its last
+ * solve: the state of OpticalFlow::GMPara (S/OpticalFlow.h:25) after the last estGaussianMixture call.  Returns the
+ * number of channels written (<= n). */
+int pf_plan_mixture_params(pf_plan* plan, double* alpha, double* sigma, double* beta, int n);
 
 /* ---- batches: N independent frame pairs sharded over devices, no collective ---
  * pair p runs on devices[p % ndevices]; im1/im2/vx/vy/warpI2 are arrays of N host pointers. */

@@ -323,6 +323,11 @@ int pf_plan_level_timings(const pf_plan* plan, double* out, int max_levels) {
     return plan->impl->level_timings(out, max_levels);
 }
 
+int pf_plan_mixture_params(pf_plan* plan, double* alpha, double* sigma, double* beta, int n) {
+    if (!plan || !alpha || !sigma || !beta || n < 1) return fail(PF_EINVAL, "bad argument");
+    return guarded([&]() -> int { return plan->impl->mixture_params(alpha, sigma, beta, n); });
+}
+
 int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im1,
                         const double* im2, double alpha, double ratio, int minWidth, int nOuter,
                         int nInner, int nSOR, int colType, int h, int w, int c, int mode, int device,

@@ -607,10 +607,23 @@ struct AssembleArgs {
     Img<T> imdx, imdy, imdt;
     const T *u, *v, *du, *dv, *phi;
     const double* lap;  // per-channel Laplacian noise scale (device), may be nullptr
+    const double* gm;   // Gaussian-mixture parameters (GmState layout, device): noiseModel == GMixture, else nullptr
     T *dxy, *iu, *iv, *bu, *bv, *dx2, *dy2;
     int w, h, pitch;
     T alpha, omega, eps;
 };
+
+// Gaussian-mixture noise model (S/NoiseModel.h:16-24): per channel alpha, sigma, beta and the two squares, in that
+// order, 16 doubles each.  The mixture arithmetic stays in double in every mode (alternative branch, not a hot path).
+constexpr int kGmStride = 16;
+enum { GM_ALPHA = 0, GM_SIGMA = 1, GM_BETA = 2, GM_SIGMA2 = 3, GM_BETA2 = 4, GM_FIELDS = 5 };
+// Quirk: the reference's Gaussian() is compiled with PI = 3.1415927 -- S/NoiseModel.h:10-12 defines its own value
+// only #ifndef PI, and S/Image.h:14 has already included S/Stochastic.h:18-20.
+#define PF_GM_PI 3.1415927
+__device__ __forceinline__ double gm_gaussian(const double* gm, double x, int i, int k) {   // S/NoiseModel.h:116-122
+    if (i == 0) return exp(-x / (2 * gm[GM_SIGMA2 * kGmStride + k])) / (2 * PF_GM_PI * gm[GM_SIGMA * kGmStride + k]);
+    return exp(-x / (2 * gm[GM_BETA2 * kGmStride + k])) / (2 * PF_GM_PI * gm[GM_BETA * kGmStride + k]);
+}
 
 template <typename T>
 __device__ __forceinline__ T laplacian_at(const T* __restrict__ in, const T* __restrict__ phi,
@@ -639,7 +652,15 @@ __global__ void k_assemble(AssembleArgs<T> a) {
         size_t oc = (size_t)y * a.imdx.pitch + x;
         T ix = a.imdx.ch(k)[oc], iy = a.imdy.ch(k)[oc], it = a.imdt.ch(k)[oc];
         T psi = 0;
-        if (!(a.lap && a.lap[k] < 1e-20)) {
+        if (a.gm) {   // S/OpticalFlow.cpp:389-396
+            double t = (double)it + (double)ix * (double)du + (double)iy * (double)dv;
+            t *= t;
+            double prob1 = gm_gaussian(a.gm, t, 0, k) * a.gm[GM_ALPHA * kGmStride + k];
+            double prob2 = gm_gaussian(a.gm, t, 1, k) * (1 - a.gm[GM_ALPHA * kGmStride + k]);
+            double prob11 = prob1 / (2 * a.gm[GM_SIGMA2 * kGmStride + k]);
+            double prob22 = prob2 / (2 * a.gm[GM_BETA2 * kGmStride + k]);
+            psi = (T)((prob11 + prob22) / (prob1 + prob2));
+        } else if (!(a.lap && a.lap[k] < 1e-20)) {
             T t = it + ix * du + iy * dv;
             t *= t;
             psi = (T)1 / ((T)2 * sqrt(t + a.eps));
@@ -703,6 +724,72 @@ static __global__ void k_noise_final(double* acc, double* lap, int c) {
     lap[k] = acc[c + k] == 0 ? 0.001 : acc[k] / acc[c + k];
     acc[k] = 0;
     acc[c + k] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// estGaussianMixture (S/OpticalFlow.cpp:539-591): three EM steps of the two-component mixture on
+// t = (Im1 - warpIm2)^2 per channel.  One step = k_gm_accum (responsibilities with the current parameters and the
+// four sums per channel: total1, total2, sum w1 t, sum w2 t -- the reference's two loops read the same weights) +
+// k_gm_update (the M step; it starts from para.reset(), :564, so the sums of sigma / beta start at 0.05 / 0.5).
+// acc = [total1[16], total2[16], s1[16], s2[16]].  Summation order differs from the reference's (rounding level).
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_gm_reset(double* gm) {   // GaussianMixture::reset, S/NoiseModel.h:98-108
+    int k = threadIdx.x;
+    if (k >= kGmStride) return;
+    gm[GM_ALPHA * kGmStride + k] = 0.95;
+    gm[GM_SIGMA * kGmStride + k] = 0.05;
+    gm[GM_BETA * kGmStride + k] = 0.5;
+    gm[GM_SIGMA2 * kGmStride + k] = 0.05 * 0.05;
+    gm[GM_BETA2 * kGmStride + k] = 0.5 * 0.5;
+}
+
+template <typename T>
+__global__ void k_gm_accum(Img<T> a, Img<T> b, const double* __restrict__ gm, double* __restrict__ acc) {
+    int k = blockIdx.z;
+    double t1 = 0, t2 = 0, s1 = 0, s2 = 0;
+    const double alpha = gm[GM_ALPHA * kGmStride + k];
+    for (int y = blockIdx.y; y < a.h; y += gridDim.y)
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.w; x += gridDim.x * blockDim.x) {
+            size_t o = (size_t)y * a.pitch + x;
+            double t = (double)a.ch(k)[o] - (double)b.ch(k)[o];
+            t *= t;
+            double w1 = gm_gaussian(gm, t, 0, k) * alpha;
+            double w2 = gm_gaussian(gm, t, 1, k) * (1 - alpha);
+            double n = w1 + w2;
+            w1 /= n;
+            w2 /= n;
+            t1 += w1; t2 += w2;
+            s1 += w1 * t; s2 += w2 * t;
+        }
+    for (int off = 16; off; off >>= 1) {
+        t1 += __shfl_down_sync(0xffffffffu, t1, off);
+        t2 += __shfl_down_sync(0xffffffffu, t2, off);
+        s1 += __shfl_down_sync(0xffffffffu, s1, off);
+        s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc + 0 * kGmStride + k, t1);
+        atomicAdd(acc + 1 * kGmStride + k, t2);
+        atomicAdd(acc + 2 * kGmStride + k, s1);
+        atomicAdd(acc + 3 * kGmStride + k, s2);
+    }
+}
+
+static __global__ void k_gm_update(double* gm, double* acc, int c) {
+    int k = threadIdx.x;
+    if (k >= c) return;
+    const double prior = 0.9;   // default argument, S/OpticalFlow.h:44
+    double t1 = acc[k], t2 = acc[kGmStride + k];
+    double sg = 0.05 + acc[2 * kGmStride + k], be = 0.5 + acc[3 * kGmStride + k];
+    double alpha = t1 / (t1 + t2) * (1 - prior) + 0.95 * prior;
+    sg = sqrt(sg / t1);
+    be = sqrt(be / t2) * (1 - prior) + 0.3 * prior;
+    gm[GM_ALPHA * kGmStride + k] = alpha;
+    gm[GM_SIGMA * kGmStride + k] = sg;
+    gm[GM_BETA * kGmStride + k] = be;
+    gm[GM_SIGMA2 * kGmStride + k] = sg * sg;
+    gm[GM_BETA2 * kGmStride + k] = be * be;
+    for (int j = 0; j < 4; j++) acc[j * kGmStride + k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

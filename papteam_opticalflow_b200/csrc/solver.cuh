@@ -29,6 +29,7 @@ struct PlanBase {
                          const double* im2, double* timings) = 0;
     virtual void profile(double* timings, double* counters) = 0;
     virtual int level_timings(double* out, int max_levels) const = 0;
+    virtual int mixture_params(double* alpha, double* sigma, double* beta, int n) = 0;   // channels written
     virtual void solve_async(int repeats) = 0;   // enqueue only
     virtual void seq_first(const unsigned char* frame) = 0;
     virtual void seq_next(const unsigned char* frame, void* out, int format) = 0;   // format: PF_SEQ_*
@@ -274,7 +275,7 @@ class Plan : public PlanBase {
         const char* e = getenv("PF_NO_GRAPH");
         use_graph_ = !(e && atoi(e)) && !lex_;
         e = getenv("PF_UNFUSED");
-        fused_ = !(e && atoi(e));
+        fused_ = !(e && atoi(e)) && P.noise != PF_NOISE_GMIXTURE;   // the mixture weight lives in the stage-by-stage path
         e = getenv("PF_FUSED_TMA");
         fused_tma_ = !(e && !atoi(e));
         if (fused_tma_)
@@ -402,6 +403,22 @@ class Plan : public PlanBase {
         }
     }
 
+    // Gaussian-mixture parameters left by the last solve (GMPara after the last estGaussianMixture call)
+    int mixture_params(double* alpha, double* sigma, double* beta, int n) override {
+        if (!gmix_) throw Error(PF_EINVAL, "plan was not created with the Gaussian-mixture noise model");
+        PF_CUDA(cudaSetDevice(P.device));
+        double host[GM_FIELDS * kGmStride];
+        PF_CUDA(cudaStreamSynchronize(st_));
+        PF_CUDA(cudaMemcpy(host, d_gm_, sizeof(host), cudaMemcpyDeviceToHost));
+        n = std::min(n, fc_);
+        for (int k = 0; k < n; k++) {
+            alpha[k] = host[GM_ALPHA * kGmStride + k];
+            sigma[k] = host[GM_SIGMA * kGmStride + k];
+            beta[k] = host[GM_BETA * kGmStride + k];
+        }
+        return n;
+    }
+
     void solve_async(int repeats) override {
         PF_CUDA(cudaSetDevice(P.device));
         for (int i = 0; i < repeats; i++) run_solve();
@@ -440,7 +457,7 @@ class Plan : public PlanBase {
         total += 10 * Arena::need(pl0 * fc_, sizeof(T));                 // f1 f2 wf s1 s2 tmp blend dx dy dt
         total += 16 * Arena::need(pl0, sizeof(T));                       // scalar planes
         if (bicubic_) total += 3 * Arena::need(pl0 * fc_, sizeof(T));    // gradients of the Im2 features (Bicubic inner warp)
-        total += Arena::need(64, sizeof(double)) * 3 + Arena::need(1, sizeof(BicubicTable));
+        total += Arena::need(64, sizeof(double)) * 3 + Arena::need(GM_FIELDS * kGmStride, sizeof(double)) + Arena::need(1, sizeof(BicubicTable));
         arena_.reserve(total + 4096);
         d_in1_ = arena_.take<double>(in_elems);
         d_in2_ = arena_.take<double>(in_elems);
@@ -470,6 +487,7 @@ class Plan : public PlanBase {
         }
         d_lap_ = arena_.take<double>(64);
         d_acc_ = arena_.take<double>(64);
+        d_gm_ = arena_.take<double>(GM_FIELDS * kGmStride);
         d_tab_ = arena_.take<BicubicTable>(1);
         d_mm_ = reinterpret_cast<unsigned int*>(arena_.take<double>(64));   // magnitude min / max of the flow visualisation
         BicubicTable tab = make_bicubic_table();
@@ -613,6 +631,11 @@ class Plan : public PlanBase {
     }
 
     void ph_lap_init() {
+        if (gmix_) {   // S/OpticalFlow.cpp:769-770
+            k_gm_reset<<<1, 32, 0, st_>>>(d_gm_);
+            launches_++;
+            return;
+        }
         if (kF64 && lex_) {
             double lap0[64];
             for (int i = 0; i < 64; i++) lap0[i] = 0.02;   // S/OpticalFlow.cpp:773-775
@@ -743,6 +766,7 @@ class Plan : public PlanBase {
             a.imdx = c.imdx; a.imdy = c.imdy; a.imdt = c.imdt;
             a.u = u_; a.v = v_; a.du = cdu; a.dv = cdv; a.phi = phi_;
             a.lap = (kF64 && lex_) ? d_lap_ : nullptr;
+            a.gm = gmix_ ? d_gm_ : nullptr;
             a.dxy = dxy_; a.iu = iu_; a.iv = iv_; a.bu = bu_; a.bv = bv_;
             a.dx2 = nullptr; a.dy2 = nullptr;
             a.w = w; a.h = h; a.pitch = pitch;
@@ -780,7 +804,13 @@ class Plan : public PlanBase {
             k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
             launches_++;
         }
-        if (kF64 && lex_) {
+        if (gmix_) {   // S/OpticalFlow.cpp:524-527
+            for (int it = 0; it < 3; it++) {
+                k_gm_accum<T><<<dim3(std::min(8, ceil_div(c.w, 128)), std::min(c.h, 64), fc_), 128, 0, st_>>>(c.f1, c.wf, d_gm_, d_acc_);
+                k_gm_update<<<1, 32, 0, st_>>>(d_gm_, d_acc_, fc_);
+                launches_ += 2;
+            }
+        } else if (kF64 && lex_) {
             k_noise_accum<T><<<dim3(std::min(8, ceil_div(c.w, 128)), std::min(c.h, 64), fc_), 128, 0, st_>>>(c.f1, c.wf, d_acc_);
             k_noise_final<<<1, 32, 0, st_>>>(d_acc_, d_lap_, fc_);
             launches_ += 2;
@@ -953,6 +983,7 @@ class Plan : public PlanBase {
     size_t span_used_ = 0;
     long long launches_ = 0, sor_launches_ = 0, sor_launches_l0_ = 0;
     double *d_in1_ = nullptr, *d_in2_ = nullptr, *d_warp_ = nullptr, *d_vx_ = nullptr, *d_vy_ = nullptr;
+    double* d_gm_ = nullptr;   // Gaussian-mixture parameters (noiseModel == GMixture)
     std::vector<Img<T>> pyr1_, pyr2_;
     T *b_tmp_ = nullptr, *b_out_ = nullptr, *b_ix_ = nullptr, *b_iy_ = nullptr, *b_ixy_ = nullptr;
     T *g_ix_ = nullptr, *g_iy_ = nullptr, *g_ixy_ = nullptr;

@@ -196,7 +196,7 @@ struct Stages {
         AssembleArgs<T> a;
         a.imdx = dx.img; a.imdy = dy.img; a.imdt = dt.img;
         a.u = U.img.p; a.v = V.img.p; a.du = du ? DU.img.p : nullptr; a.dv = dv ? DV.img.p : nullptr;
-        a.phi = phi.img.p; a.lap = dlap;
+        a.phi = phi.img.p; a.lap = dlap; a.gm = nullptr;
         a.dxy = dxy.img.p; a.iu = iu.img.p; a.iv = iv.img.p; a.bu = bu.img.p; a.bv = bv.img.p;
         a.dx2 = dx2.img.p; a.dy2 = dy2.img.p;
         a.w = w; a.h = h; a.pitch = U.img.pitch;

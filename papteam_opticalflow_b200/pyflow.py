@@ -154,6 +154,14 @@ class FlowPlan(object):
             check(_lib.lib().pf_plan_profile(self._h, _ptr(t), _ptr(cnt)))
         return t, cnt
 
+    def mixture_params(self):
+        """(alpha, sigma, beta) per feature channel after the last solve (Gaussian-mixture noise model only)."""
+        a, s, b = np.zeros(16), np.zeros(16), np.zeros(16)
+        n = _lib.lib().pf_plan_mixture_params(self._h, _ptr(a), _ptr(s), _ptr(b), 16)
+        if n < 0:
+            check(n)
+        return a[:n].copy(), s[:n].copy(), b[:n].copy()
+
     def level_timings(self):
         """(levels, PF_NUM_TIMINGS) array of per-level phase milliseconds from the last profile()."""
         out = np.zeros((self.levels, _lib.PF_NUM_TIMINGS))

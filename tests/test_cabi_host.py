@@ -113,3 +113,21 @@ def test_product_never_references_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for bad in ("import oracle", "from oracle", "oracle/", "oracle.", "liboracle", "_ref/", "pyflow_ref"):
                     assert bad not in txt, (os.path.join(dirpath, f), bad)
+
+
+def test_solver_variant_switch_is_host_only_and_validated():
+    """pf_set_solver_variant mirrors the reference's process-global statics (S/OpticalFlow.h:19-27); no GPU needed."""
+    import pyflow
+    assert pyflow.get_solver_variant() == ("bilinear", "lap")   # the reference's defaults, S/OpticalFlow.cpp:33-34
+    try:
+        pyflow.set_solver_variant("bicubic", "gmixture")
+        assert pyflow.get_solver_variant() == ("bicubic", "gmixture")
+        with pytest.raises(ValueError):
+            pyflow.set_solver_variant("nearest", "lap")
+        with pytest.raises(ValueError):
+            pyflow.set_solver_variant("bilinear", "gaussian")
+        assert pyflow.get_solver_variant() == ("bicubic", "gmixture")
+        from papteam_opticalflow_b200 import _lib
+        assert _lib.lib().pf_set_solver_variant(7, 1) == _lib.PF_EINVAL
+    finally:
+        pyflow.set_solver_variant("bilinear", "lap")
