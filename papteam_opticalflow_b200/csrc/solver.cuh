@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "sor.cuh"
 #include "fused_tma.cuh"
+#include "staging.hpp"
 
 namespace pf {
 
@@ -299,19 +300,39 @@ class Plan : public PlanBase {
 
     int levels() const override { return nlev_; }
 
+    // Host buffers are the caller's numpy arrays (pageable) or pinned memory.  Pageable ones of a useful size go
+    // through the multi-threaded stager (staging.hpp), pinned ones straight to the copy engine.
+    static constexpr size_t kStageMinBytes = 8u << 20;
+
     void upload(const double* im1, const double* im2) override {
         PF_CUDA(cudaSetDevice(P.device));
         size_t n = (size_t)P.h * P.w * P.c * sizeof(double);
+        HostStager* hs = (2 * n >= kStageMinBytes && host_is_pageable(im1) && host_is_pageable(im2)) ? HostStager::for_device(P.device) : nullptr;
+        if (hs) {
+            hs->to_device({{d_in1_, const_cast<double*>(im1), n}, {d_in2_, const_cast<double*>(im2), n}}, st_);
+            return;
+        }
         PF_CUDA(cudaMemcpyAsync(d_in1_, im1, n, cudaMemcpyHostToDevice, st_));
         PF_CUDA(cudaMemcpyAsync(d_in2_, im2, n, cudaMemcpyHostToDevice, st_));
     }
 
-    void download(double* vx, double* vy, double* warp) override {
-        PF_CUDA(cudaSetDevice(P.device));
+    // enqueue (pinned destinations) or perform (pageable destinations) the three output copies
+    void download_outputs(double* vx, double* vy, double* warp) {
         size_t n = (size_t)P.h * P.w * sizeof(double);
+        HostStager* hs = ((2 + P.c) * n >= kStageMinBytes && host_is_pageable(vx) && host_is_pageable(vy) && host_is_pageable(warp))
+                                 ? HostStager::for_device(P.device) : nullptr;
+        if (hs) {
+            hs->to_host({{d_vx_, vx, n}, {d_vy_, vy, n}, {d_warp_, warp, n * P.c}}, st_);
+            return;
+        }
         PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
         PF_CUDA(cudaMemcpyAsync(vy, d_vy_, n, cudaMemcpyDeviceToHost, st_));
         PF_CUDA(cudaMemcpyAsync(warp, d_warp_, n * P.c, cudaMemcpyDeviceToHost, st_));
+    }
+
+    void download(double* vx, double* vy, double* warp) override {
+        PF_CUDA(cudaSetDevice(P.device));
+        download_outputs(vx, vy, warp);
         PF_CUDA(cudaStreamSynchronize(st_));
     }
 
@@ -338,10 +359,7 @@ class Plan : public PlanBase {
         run_solve();
         const auto h2 = std::chrono::steady_clock::now();
         PF_CUDA(cudaEventRecord(ev_[2], st_));
-        size_t n = (size_t)P.h * P.w * sizeof(double);
-        PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
-        PF_CUDA(cudaMemcpyAsync(vy, d_vy_, n, cudaMemcpyDeviceToHost, st_));
-        PF_CUDA(cudaMemcpyAsync(warp, d_warp_, n * P.c, cudaMemcpyDeviceToHost, st_));
+        download_outputs(vx, vy, warp);
         PF_CUDA(cudaEventRecord(ev_[3], st_));
         PF_CUDA(cudaStreamSynchronize(st_));
         if (timings) {
