@@ -321,9 +321,16 @@ struct SorStage {
 #ifndef PF_SORX
 #define PF_SORX 0
 #endif
+#ifdef PF_SOR_MAXREG
+template <typename T, int R, int NW>
+__global__ void __maxnreg__(sizeof(T) == 4 ? PF_SOR_MAXREG : 128)
+k_sor_rb_tma(
+#else
 template <typename T, int R, int NW>
 __global__ void __launch_bounds__(NW * 32, PF_SOR_MINB)
-k_sor_rb_tma(const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
+k_sor_rb_tma(
+#endif
+const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv_out, int W, int H, int P,
              T alpha, T omega, int nsw, int has_input, int ntx, int nty, int step_x, int step_y, int ty0, SorPeer<T> peer) {
     static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
     typedef typename Vec2<T>::type V2;
