@@ -190,12 +190,16 @@ int pf_sequence_flow_u8_bgr(int nframes, const unsigned char* const* frames, uns
 int pf_flow_to_bgr(const float* flow, unsigned char* bgr, int h, int w, int device);
 
 /* ---- ONE large pair over several GPUs (BASELINE config 5): every device runs the
- * cheap stages redundantly, the SOR solve is split into row bands with peer-to-peer halo exchange
- * over NVLink after every fused-sweep pass (cudaMemcpyPeerAsync ordered by events, no collective).
+ * cheap stages redundantly, the SOR solve is split into row bands whose halo rows -- and, after the
+ * last pass, whole bands -- are stored by the SOR kernel itself into the neighbours' planes (peer-mapped
+ * pointers over NVLink); passes are ordered by device-side counters in peer memory when every band has its
+ * own GPU, by stream events otherwise; rows a non-adjacent band needs are fetched by a copy kernel.  No
+ * collective, and the launch sequence of all devices is ONE CUDA graph.
  * FP32 red-black mode only; the result is bit-identical to the single-GPU fast mode.  Levels with
  * fewer than split_min_pixels pixels (<0: default 2000000) are solved redundantly.  devices may
  * repeat an index (bands then share one GPU -- used by the single-GPU tests of the exchange logic).
- * stats (may be NULL, 4 doubles): solve ms, halo bytes pulled, gather bytes pulled, split solves. */
+ * stats (may be NULL, 8 doubles): solve ms, halo bytes exchanged, gather bytes exchanged, split solves,
+ * 1 if the solve was one multi-device graph replay, split solves ordered by device-side flags, 0, 0. */
 int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, const double* im2,
                      double alpha, double ratio, int minWidth, int levels, int nOuterFPIterations,
                      int nInnerFPIterations, int nSORIterations, int colType, int h, int w, int c,

@@ -10,6 +10,12 @@
 // collective).  After the last pass every device gathers the other bands so that the replicated
 // update + warp stage sees the complete du, dv.  The red-black update is independent of the tiling, so
 // the result equals the single-GPU result bit for bit.
+// Between the passes of one solve the bands are ordered by DEVICE-SIDE FLAGS when every band has its own
+// GPU: the CTAs of a pass bump counters in the neighbours' memory when they are done and the neighbours'
+// next pass spins on them (SorPeer, sor.cuh) -- a cross-device stream-event edge costs about as much as a
+// whole pass of a 4K level (~60 us), a flag in peer memory a few microseconds.  Stream events still open
+// every split solve and order its final gather.  Bands that share a GPU (tests) keep the event path: a
+// spinning persistent kernel would occupy the SMs its producer needs.
 // Levels below `split_min_pixels` are solved redundantly on every device (no exchange at all).
 // The lexicographic parity mode does not band-split (band b would wait for band b-1 in every sweep):
 // replicas only.
@@ -18,6 +24,11 @@
 #include "solver.cuh"
 
 namespace pf {
+
+// grid-stride 16-byte copy; `src` may be a peer-mapped pointer (loads travel over NVLink)
+static __global__ void k_copy_peer(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 
 class MultiPlan {
   public:
@@ -50,11 +61,35 @@ class MultiPlan {
         }
         PF_CUDA(cudaSetDevice(devs_[0]));
         PF_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+        // device-side flags need one GPU per band and peer access between neighbouring bands
+        e = getenv("PF_MULTI_FLAGS");
+        flags_ok_ = push_ && !(e && !atoi(e)) && ndev > 1;
+        for (int g = 0; g < ndev && flags_ok_; g++) {
+            for (int h = 0; h < g; h++)
+                if (devs_[h] == devs_[g]) flags_ok_ = false;
+            if (g + 1 < ndev && flags_ok_) {
+                int a = 0, b = 0;
+                PF_CUDA(cudaDeviceCanAccessPeer(&a, devs_[g], devs_[g + 1]));
+                PF_CUDA(cudaDeviceCanAccessPeer(&b, devs_[g + 1], devs_[g]));
+                if (!a || !b) flags_ok_ = false;
+            }
+        }
+        if (flags_ok_) {
+            flags_.assign((size_t)ndev, nullptr);
+            for (int g = 0; g < ndev; g++) {
+                PF_CUDA(cudaSetDevice(devs_[g]));
+                PF_CUDA(cudaMalloc(&flags_[(size_t)g], kFlagSlots * 2 * sizeof(unsigned int)));
+            }
+        }
     }
     ~MultiPlan() {
         if (gexec_) cudaGraphExecDestroy(gexec_);
         if (graph_) cudaGraphDestroy(graph_);
         if (ev_fork_) cudaEventDestroy(ev_fork_);
+        for (size_t g = 0; g < flags_.size(); g++) {
+            cudaSetDevice(devs_[g]);
+            if (flags_[g]) cudaFree(flags_[g]);
+        }
         for (size_t g = 0; g < devs_.size(); g++) {
             cudaSetDevice(devs_[g]);
             cudaEventDestroy(ev_pass_[g]);
@@ -83,7 +118,12 @@ class MultiPlan {
             stats[1] = (double)halo_bytes_;
             stats[2] = (double)gather_bytes_;
             stats[3] = (double)split_solves_;
+            stats[4] = gexec_ ? 1.0 : 0.0;       // the whole multi-device launch sequence was one CUDA graph replay
+            stats[5] = (double)flag_solves_;     // split solves whose passes were ordered by device-side flags
         }
+        if (getenv("PF_MULTI_TRACE"))
+            fprintf(stderr, "pyflow_b200 multigpu [%s]: %.3f ms, %d split solves (%d ordered by device-side flags, %d flag slots), halo %.1f MB, gather %.1f MB\n",
+                    gexec_ ? "one multi-device graph" : "eager", ms, split_solves_, flag_solves_, flag_slot_, halo_bytes_ / 1e6, gather_bytes_ / 1e6);
         return ms;
     }
 
@@ -116,7 +156,8 @@ class MultiPlan {
                     on(0);
                     PF_CUDA(cudaStreamEndCapture(s0, &graph_));
                     PF_CUDA(cudaGraphInstantiate(&gexec_, graph_, 0));
-                } catch (const Error&) {
+                } catch (const Error& err) {
+                    if (getenv("PF_MULTI_TRACE")) fprintf(stderr, "pyflow_b200 multigpu: graph capture failed: %s\n", err.what());
                     cudaGraph_t g = nullptr;
                     cudaStreamEndCapture(s0, &g);
                     if (g) cudaGraphDestroy(g);
@@ -125,6 +166,7 @@ class MultiPlan {
                     gexec_ = nullptr;
                 }
             } else {
+                if (getenv("PF_MULTI_TRACE")) fprintf(stderr, "pyflow_b200 multigpu: cudaStreamBeginCapture failed: %s\n", cudaGetErrorString(st));
                 cudaGetLastError();
                 graph_failed_ = true;
             }
@@ -147,6 +189,13 @@ class MultiPlan {
         const int G = (int)devs_.size();
         halo_bytes_ = gather_bytes_ = 0;
         split_solves_ = 0;
+        flag_slot_ = 0;
+        flag_solves_ = 0;
+        if (flags_ok_)   // counters start at zero in every solve (the first split solve's opening barrier orders this)
+            for (int g = 0; g < G; g++) {
+                on(g);
+                PF_CUDA(cudaMemsetAsync(flags_[(size_t)g], 0, kFlagSlots * 2 * sizeof(unsigned int), plans_[g]->stream()));
+            }
         for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_begin(); }
         const int nlev = plans_[0]->levels();
         for (int k = nlev - 1; k >= 0; k--) {
@@ -163,11 +212,21 @@ class MultiPlan {
         for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_end(); }
     }
 
-    // rows [r0, r1) of plane `src` on device hs -> same rows of plane `dst` on device hd, on hd's stream
+    // rows [r0, r1) of plane `src` on device hs -> same rows of plane `dst` on device hd, on hd's stream.
+    // Between different GPUs a copy KERNEL on the destination reads the peer-mapped source over NVLink:
+    // cudaMemcpyPeerAsync is not permitted while a stream is capturing, and the whole multi-device launch
+    // sequence has to stay one CUDA graph (an eager 2-GPU solve is bound by the host issuing ~10^4 launches).
     void pull_rows(int hd, float* dst, int hs, const float* src, int r0, int r1, int pitch, long long& counter) {
         if (r1 <= r0) return;
         size_t off = (size_t)r0 * pitch, bytes = (size_t)(r1 - r0) * pitch * sizeof(float);
-        PF_CUDA(cudaMemcpyPeerAsync(dst + off, devs_[hd], src + off, devs_[hs], bytes, plans_[hd]->stream()));
+        if (devs_[hd] == devs_[hs]) {
+            PF_CUDA(cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyDeviceToDevice, plans_[hd]->stream()));
+        } else {
+            const size_t n4 = bytes / sizeof(float4);   // rows are padded to 128-byte multiples
+            const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+            k_copy_peer<<<blocks, 256, 0, plans_[hd]->stream()>>>(reinterpret_cast<float4*>(dst + off),
+                                                                   reinterpret_cast<const float4*>(src + off), n4);
+        }
         counter += (long long)bytes;
     }
 
@@ -205,6 +264,22 @@ class MultiPlan {
         };
         struct Range { int lo, hi; };
         auto cut = [](Range a, Range b) { return Range{std::max(a.lo, b.lo), std::min(a.hi, b.hi)}; };
+        // device-side flags between the passes of this solve: possible when every row a band needs from another band
+        // comes from an ADJACENT one (then the producing kernel pushes exactly those rows) and counters are left
+        bool use_flags = flags_ok_ && sched.size() > 1 && flag_slot_ + (int)sched.size() <= kFlagSlots;
+        for (size_t p = 0; p + 1 < sched.size() && use_flags; p++)
+            for (int g = 0; g < G && use_flags; g++) {
+                int tb, te;
+                band(sched[p + 1], g, tb, te);
+                const Range need_g{sched[p + 1].in_lo(tb), sched[p + 1].in_hi(te - 1, h)};
+                for (int o = 0; o < G; o++) {
+                    if (o == g || o == g - 1 || o == g + 1) continue;
+                    band(sched[p], o, tb, te);
+                    const Range r = cut(need_g, Range{sched[p].out_lo(tb), sched[p].out_hi(te - 1, h)});
+                    if (r.hi > r.lo) use_flags = false;
+                }
+            }
+        if (use_flags) flag_solves_++;
         for (size_t p = 0; p < sched.size(); p++) {
             const Runner::SorPass& ps = sched[p];
             const bool last = p + 1 == sched.size();
@@ -230,7 +305,9 @@ class MultiPlan {
                 int tb, te;
                 band(ps, g, tb, te);
                 SorPeer<float> peer;
-                if (!last && push_) {
+                // (after the last pass the neighbours need the WHOLE band: the kernel's own stores replace the gather
+                // between adjacent bands -- with two GPUs no separate copy is left)
+                if (push_) {
                     if (g > 0) {
                         Range r = cut(need[g - 1], own[g]);
                         if (r.hi > r.lo) { peer.up_du = out_u[g - 1]; peer.up_dv = out_v[g - 1]; peer.up_lo = r.lo; peer.up_hi = r.hi; pushed_up[g] = r; }
@@ -239,7 +316,27 @@ class MultiPlan {
                         Range r = cut(need[g + 1], own[g]);
                         if (r.hi > r.lo) { peer.dn_du = out_u[g + 1]; peer.dn_dv = out_v[g + 1]; peer.dn_lo = r.lo; peer.dn_hi = r.hi; pushed_dn[g] = r; }
                     }
-                    halo_bytes_ += 2LL * ((peer.up_hi - peer.up_lo) + (peer.dn_hi - peer.dn_lo)) * w * (long long)sizeof(float);
+                    (last ? gather_bytes_ : halo_bytes_) += 2LL * ((peer.up_hi - peer.up_lo) + (peer.dn_hi - peer.dn_lo)) * w * (long long)sizeof(float);
+                }
+                if (use_flags) {
+                    const int slot = flag_slot_ + (int)p;
+                    if (p > 0) {          // the neighbours' previous pass: counters of slot - 1 in OUR memory
+                        int nb, ne;
+                        if (g > 0) {
+                            band(sched[p - 1], g - 1, nb, ne);
+                            peer.wait_flag[0] = flags_[(size_t)g] + 2 * (slot - 1) + 0;
+                            peer.wait_count[0] = (unsigned)v[g - 1].runner->grid_for(sched[p - 1], ne - nb);
+                        }
+                        if (g + 1 < G) {
+                            band(sched[p - 1], g + 1, nb, ne);
+                            peer.wait_flag[1] = flags_[(size_t)g] + 2 * (slot - 1) + 1;
+                            peer.wait_count[1] = (unsigned)v[g + 1].runner->grid_for(sched[p - 1], ne - nb);
+                        }
+                    }
+                    if (!last) {          // our arrival: the upper neighbour's "from below" counter, the lower one's "from above"
+                        if (g > 0) peer.signal_flag[0] = flags_[(size_t)g - 1] + 2 * slot + 1;
+                        if (g + 1 < G) peer.signal_flag[1] = flags_[(size_t)g + 1] + 2 * slot + 0;
+                    }
                 }
                 v[g].runner->launch_pass(v[g].args, ps, in_u[g], in_v[g], out_u[g], out_v[g], tb, te, peer);
                 PF_CUDA(cudaEventRecord(ev_pass_[g], plans_[g]->stream()));
@@ -248,6 +345,7 @@ class MultiPlan {
                 std::swap(*v[g].du, *v[g].du2);
                 std::swap(*v[g].dv, *v[g].dv2);
             }
+            if (use_flags && !last) continue;   // the next pass waits on the neighbours' counters inside the kernel
             // whatever a device still misses is pulled from its owner; pushes only need the event
             for (int g = 0; g < G; g++) {
                 on(g);
@@ -268,8 +366,10 @@ class MultiPlan {
                 }
             }
         }
+        if (use_flags) flag_slot_ += (int)sched.size();
     }
 
+    static constexpr int kFlagSlots = 1 << 14;   // passes of all split solves of one pair (two counters each)
     Params P;
     long long split_min_;
     std::vector<int> devs_;
@@ -282,6 +382,9 @@ class MultiPlan {
     cudaEvent_t ev_fork_ = nullptr;
     bool graph_failed_ = false;
     bool push_ = true;     // halo rows stored by the producing kernel into the neighbour (PF_MULTI_PULL=1: copy-engine pulls)
+    bool flags_ok_ = false;                 // one GPU per band with peer access: passes ordered by device-side counters
+    std::vector<unsigned int*> flags_;      // per device: kFlagSlots x {from above, from below}
+    int flag_slot_ = 0, flag_solves_ = 0;
 };
 
 }  // namespace pf

@@ -191,6 +191,9 @@ struct SorRunner {
         return v;
     }
 
+    // CTAs of a launch over `nrows` tile rows of pass `ps` (persistent kernel: at most one wave)
+    int grid_for(const SorPass& ps, int nrows) const { return std::min(ps.tx.ntiles * nrows, sms * ctas_per_sm); }
+
     // tile rows [ty_begin, ty_end) of one pass: reads du/dv (if has_input), writes du2/dv2
     void launch_pass(SorArgs<T> a, const SorPass& ps, T* du, T* dv, T* du2, T* dv2, int ty_begin, int ty_end,
                      const SorPeer<T>& peer = SorPeer<T>()) {
@@ -208,9 +211,8 @@ struct SorRunner {
             m.bv = make_plane_map(a.bv, w, h, a.pitch, kSorRegionW, kRegionH);
             m.du = make_plane_map(ps.has_input ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
             m.dv = make_plane_map(ps.has_input ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
-            int ntiles = ps.tx.ntiles * nrows;
             size_t smem = sor_smem_bytes();
-            k_sor_rb_tma<T, kR, kNW><<<std::min(ntiles, sms * ctas_per_sm), kNW * 32, smem, st>>>(
+            k_sor_rb_tma<T, kR, kNW><<<grid_for(ps, nrows), kNW * 32, smem, st>>>(
                     m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
                     ps.tx.step, ps.ty.step, ty_begin, peer);
         } else {

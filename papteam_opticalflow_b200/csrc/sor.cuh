@@ -300,11 +300,29 @@ struct SorMaps {
 // upper neighbour's output planes and rows [dn_lo, dn_hi) into the lower neighbour's (peer-mapped
 // pointers, posted stores over NVLink), which is the halo the neighbour's next pass reads.  Empty
 // ranges / null pointers on a single GPU.
+//
+// Ordering between the passes of neighbouring bands without the host or stream events: every CTA of a pass bumps a
+// counter in each neighbour's memory once its stores (own planes and pushed halo rows) are out (release, system
+// scope); the CTAs of the neighbour's NEXT pass spin on that counter (acquire) until all CTAs of this pass have
+// arrived, before they issue their first tile load.  wait[0] / signal[0] belong to the upper neighbour, [1] to the
+// lower one; null pointers = no such neighbour / first or last pass of a solve (those are ordered by events).
 template <typename T>
 struct SorPeer {
     T *up_du = nullptr, *up_dv = nullptr, *dn_du = nullptr, *dn_dv = nullptr;
     int up_lo = 0, up_hi = 0, dn_lo = 0, dn_hi = 0;
+    unsigned int* wait_flag[2] = {nullptr, nullptr};     // counters in THIS device's memory
+    unsigned int wait_count[2] = {0, 0};                 // CTAs of the neighbour's previous pass
+    unsigned int* signal_flag[2] = {nullptr, nullptr};   // counters in the neighbours' memory (peer mapped)
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <typename T, int R, int NW>
 struct SorStage {
@@ -372,6 +390,24 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
     if (tid == 0) {
         mbar_init(&full_bar, 1);
         mbar_fence_init();
+    }
+    // row-band split: the neighbours' previous pass must be complete (its halo rows are in our input planes, and
+    // it no longer reads the planes this pass pushes into) before anything of this pass touches memory
+    if (peer.wait_flag[0] || peer.wait_flag[1]) {
+        if (tid == 0) {
+            for (int side = 0; side < 2; side++) {
+                if (!peer.wait_flag[side]) continue;
+                unsigned int spins = 0;
+                while (ld_acquire_sys(peer.wait_flag[side]) < peer.wait_count[side]) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 22)) {   // a lost neighbour must not hang the GPU (a few seconds)
+                        printf("pyflow_b200: row-band neighbour timeout (block %d side %d)\n", blockIdx.x, side);
+                        __trap();
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // the tile loads below go through the async proxy
+        }
     }
     __syncthreads();
     int tile = blockIdx.x;
@@ -547,6 +583,15 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
                     }
                 }
             }
+        }
+    }
+    // row-band split: this CTA is done reading and writing -- tell the neighbours (one arrival per CTA)
+    if (peer.signal_flag[0] || peer.signal_flag[1]) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (peer.signal_flag[0]) red_release_sys_add(peer.signal_flag[0], 1u);
+            if (peer.signal_flag[1]) red_release_sys_add(peer.signal_flag[1], 1u);
         }
     }
 }

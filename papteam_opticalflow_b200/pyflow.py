@@ -349,7 +349,7 @@ def coarse2fine_flow_multigpu(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nO
     """ONE pair solved by several GPUs: the SOR solve of the fine levels is split into row bands with
     NVLink peer-to-peer halo exchange (pf_multigpu_flow; FP32 red-black mode, bit-identical to the
     single-GPU fast mode).  Returns (u, v, im2W, stats) with stats = dict(ms, halo_bytes, gather_bytes,
-    split_solves)."""
+    split_solves, graph, flag_solves)."""
     L = _lib.lib()
     _check_image("Im1", im1)
     _check_image("Im2", im2)
@@ -360,11 +360,12 @@ def coarse2fine_flow_multigpu(im1, im2, alpha=0.012, ratio=0.75, minWidth=20, nO
     h, w, c = im1.shape
     vx, vy, wi = np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))
     dev = (C.c_int * len(devices))(*devices)
-    st = np.zeros(4)
+    st = np.zeros(8)
     check(L.pf_multigpu_flow(_ptr(vx), _ptr(vy), _ptr(wi), _ptr(im1), _ptr(im2), float(alpha), float(ratio), int(minWidth),
                              int(levels), int(nOuterFPIterations), int(nInnerFPIterations), int(nSORIterations),
                              int(colType), h, w, c, dev, len(devices), int(split_min_pixels), _ptr(st)))
-    return vx, vy, wi, dict(ms=st[0], halo_bytes=int(st[1]), gather_bytes=int(st[2]), split_solves=int(st[3]))
+    return vx, vy, wi, dict(ms=st[0], halo_bytes=int(st[1]), gather_bytes=int(st[2]), split_solves=int(st[3]),
+                            graph=bool(st[4]), flag_solves=int(st[5]))
 
 
 def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7,

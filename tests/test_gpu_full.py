@@ -316,6 +316,20 @@ def test_row_band_split_on_real_peers_if_present():
     u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=list(range(min(n, 4))), split_min_pixels=50000)
     assert st["split_solves"] > 0
     assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+    # on real peers the launch sequence of all devices must still be ONE graph (cudaMemcpyPeerAsync cannot be
+    # captured: the exchange uses kernels) and the passes are ordered by device-side flags
+    assert st["graph"] and st["flag_solves"] == st["split_solves"]
+    # the stream-event ordering stays available and gives the same bits
+    import os
+    os.environ["PF_MULTI_FLAGS"] = "0"
+    try:
+        a2, b2 = np.ascontiguousarray(a[:-2]), np.ascontiguousarray(b[:-2])   # another shape: a fresh MultiPlan reads the switch
+        u1, v1, _ = pyflow.coarse2fine_flow(a2, b2, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+        u, v, _, st = pyflow.coarse2fine_flow_multigpu(a2, b2, devices=list(range(min(n, 4))), split_min_pixels=50000)
+    finally:
+        del os.environ["PF_MULTI_FLAGS"]
+    assert st["split_solves"] > 0 and st["flag_solves"] == 0 and st["graph"]
+    assert np.array_equal(u, u1) and np.array_equal(v, v1)
 
 
 def _u8_frame(width, idx):
