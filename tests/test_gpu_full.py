@@ -427,3 +427,25 @@ def test_sequence_mode_bgr_output_is_the_visualisation_of_its_flow():
         assert im.max() == 255              # min-max normalisation: the fastest pixel has full value
     with pytest.raises(ValueError):
         pyflow.sequence_flow(frames, output="png")
+
+
+def test_pageable_buffers_through_the_stager_equal_the_direct_copy_path(monkeypatch):
+    """One-shot calls move pageable numpy buffers through the multi-threaded pinned-slot stager (csrc/staging.hpp) when
+    they are large enough; PF_STAGER=0 keeps plain cudaMemcpyAsync.  Same bits either way, also when the byte counts are
+    not multiples of the 4 MB chunk and when the buffers are reused across calls."""
+    a, b = load_frame(960, 1), load_frame(960, 2)
+    a2, b2 = np.ascontiguousarray(a[:-7, :-5]), np.ascontiguousarray(b[:-7, :-5])   # 533 x 955: ragged chunks
+    monkeypatch.setenv("PF_STAGER", "0")
+    want = pyflow.coarse2fine_flow(a2, b2, 0.012, 0.75, 20, 3, 1, 10, 0, mode="fp32_redblack")
+    monkeypatch.setenv("PF_STAGER", "1")
+    for _ in range(3):
+        got = pyflow.coarse2fine_flow(a2, b2, 0.012, 0.75, 20, 3, 1, 10, 0, mode="fp32_redblack")
+        for x, y in zip(got, want):
+            assert np.array_equal(x, y)
+    # alternating inputs: a stale slot or a missed event would leak the previous pair into this one
+    want_ba = pyflow.coarse2fine_flow(b2, a2, 0.012, 0.75, 20, 3, 1, 10, 0, mode="fp32_redblack")
+    monkeypatch.setenv("PF_STAGER", "0")
+    ref_ba = pyflow.coarse2fine_flow(b2, a2, 0.012, 0.75, 20, 3, 1, 10, 0, mode="fp32_redblack")
+    for x, y in zip(want_ba, ref_ba):
+        assert np.array_equal(x, y)
+    assert np.abs(want_ba[0] - want[0]).max() > 1e-3
