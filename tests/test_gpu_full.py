@@ -449,3 +449,28 @@ def test_pageable_buffers_through_the_stager_equal_the_direct_copy_path(monkeypa
     for x, y in zip(want_ba, ref_ba):
         assert np.array_equal(x, y)
     assert np.abs(want_ba[0] - want[0]).max() > 1e-3
+
+
+def test_multi_pass_sor_kernel_is_bit_identical(monkeypatch):
+    """PF_SOR_MULTI=1 runs all fused-sweep passes of a solve in ONE launch of k_sor_rb_multi (tile-level dependencies
+    through per-tile pass counters instead of kernel boundaries; opt-in).  The red-black update does
+    not depend on tiling or pass structure: same bits as the default path, also with a sweep count that leaves a short
+    last pass."""
+    import subprocess, sys, os
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import pyflow; from conftest import load_frame\n"
+        "a, b = load_frame(960, 1), load_frame(960, 2)\n"
+        "out = []\n"
+        "for nsor in (30, 17):\n"
+        "    u, v, w = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 3, 1, nsor, 0, mode='fp32_redblack')\n"
+        "    out += [u, v]\n"
+        "np.save(sys.argv[1], np.stack(out))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for flag in ("0", "1"):   # the switch is read when the library initialises a solver: one process per setting
+        path = "/tmp/pf_multi_%s.npy" % flag
+        env = dict(os.environ, PF_SOR_MULTI=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[flag] = np.load(path)
+    assert np.array_equal(res["0"], res["1"])
