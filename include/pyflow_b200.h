@@ -50,6 +50,14 @@ extern "C" {
 #define PF_NOISE_GMIXTURE  0
 #define PF_NOISE_LAP       1
 
+/* ---- schedule tuning: how many red-black sweeps one launch of the SOR kernel fuses is chosen per pyramid level from a
+ *      cost model with two fits (the result is bit-identical either way: the red-black update does not depend on the
+ *      tiling).  THROUGHPUT minimises SM time -- right when many pairs are in flight (batches, sequences, explicit
+ *      plans run concurrently); LATENCY minimises the time of one pair alone -- used by the one-shot entry points.
+ *      Environment PF_SOR_TUNE=latency|throughput forces one fit everywhere. */
+#define PF_TUNE_THROUGHPUT 0
+#define PF_TUNE_LATENCY    1
+
 /* ---- timing report: the reference's timing-map keys (S/OpticalFlow.cpp:850-860), in
  *      milliseconds of GPU time from CUDA events, plus the transfer legs ---------------------- */
 enum {
@@ -115,6 +123,10 @@ int pf_pool_clear(void);
 int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
                    int levels, int nOuterFPIterations, int nInnerFPIterations, int nSORIterations,
                    int colType, int mode, int device);
+/* pf_plan_create uses PF_TUNE_THROUGHPUT; this one takes the tuning explicitly. */
+int pf_plan_create_tuned(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                         int levels, int nOuterFPIterations, int nInnerFPIterations, int nSORIterations,
+                         int colType, int mode, int device, int tuning);
 int pf_plan_destroy(pf_plan* plan);
 int pf_plan_levels(const pf_plan* plan);
 /* H2D + solve + D2H with host buffers (pageable or pinned). */

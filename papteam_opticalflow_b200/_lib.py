@@ -51,6 +51,7 @@ def lib():
         "pf_set_solver_variant": (i, [i, i]),
         "pf_get_solver_variant": (i, [ip, ip]),
         "pf_plan_create": (i, [C.POINTER(v), i, i, i, d, d, i, i, i, i, i, i, i, i]),
+        "pf_plan_create_tuned": (i, [C.POINTER(v), i, i, i, d, d, i, i, i, i, i, i, i, i, i]),
         "pf_plan_destroy": (i, [v]),
         "pf_plan_levels": (i, [v]),
         "pf_plan_execute": (i, [v, dp, dp, dp, dp, dp, dp]),

@@ -103,8 +103,8 @@ void pool_release(pf_plan* pl) {
 
 }  // namespace
 
-extern "C" int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
-                              int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device);
+extern "C" int pf_plan_create_tuned(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                                    int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device, int tuning);
 extern "C" int pf_plan_destroy(pf_plan* plan);
 
 namespace {
@@ -131,8 +131,8 @@ pf_plan* pool_acquire(const Params& p, int& rc) {
     }
     for (pf_plan* e : evict) pf_plan_destroy(e);
     pf_plan* pl = nullptr;
-    rc = pf_plan_create(&pl, p.h, p.w, p.c, p.alpha, p.ratio, p.min_width, p.levels, p.n_outer, p.n_inner, p.n_sor,
-                        p.col_type, p.mode, p.device);
+    rc = pf_plan_create_tuned(&pl, p.h, p.w, p.c, p.alpha, p.ratio, p.min_width, p.levels, p.n_outer, p.n_inner, p.n_sor,
+                              p.col_type, p.mode, p.device, p.tune);
     if (rc) return nullptr;
     std::lock_guard<std::mutex> g(g_pool_mu);
     g_pool.push_back(PoolEntry{p, pl, true, ++g_pool_clock});
@@ -207,9 +207,16 @@ int pf_level_geometry(int w, int h, double ratio, int levels, int* widths, int* 
 
 int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
                    int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device) {
+    return pf_plan_create_tuned(plan, h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, device,
+                                PF_TUNE_THROUGHPUT);
+}
+
+int pf_plan_create_tuned(pf_plan** plan, int h, int w, int c, double alpha, double ratio, int minWidth,
+                         int levels, int nOuter, int nInner, int nSOR, int colType, int mode, int device, int tuning) {
     return guarded([&]() -> int {
         if (!plan) return fail(PF_EINVAL, "plan is NULL");
         *plan = nullptr;
+        if (tuning != PF_TUNE_THROUGHPUT && tuning != PF_TUNE_LATENCY) return fail(PF_EINVAL, "tuning must be PF_TUNE_THROUGHPUT or PF_TUNE_LATENCY");
         int r;
         if ((r = check_image(h, w, c)) || (r = check_mode(mode))) return r;
         if (nOuter < 0 || nInner < 0 || nSOR < 0) return fail(PF_EINVAL, "iteration counts must be non-negative");
@@ -217,6 +224,7 @@ int pf_plan_create(pf_plan** plan, int h, int w, int c, double alpha, double rat
         if (!(alpha == alpha) || !(ratio == ratio) || ratio <= 0) return fail(PF_EINVAL, "alpha/ratio invalid");
         if ((r = check_device(device))) return r;
         Params p{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, device};
+        p.tune = tuning;
         std::unique_ptr<pf_plan> pl(new pf_plan);
         pl->impl.reset(make_plan(p));
         *plan = pl.release();
@@ -334,6 +342,7 @@ int pf_coarse2fine_flow(double* vx, double* vy, double* warpI2, const double* im
                         double* timings) {
     int r = PF_OK;
     Params p{h, w, c, alpha, ratio, minWidth, 0, nOuter, nInner, nSOR, colType, mode, device};
+    p.tune = PF_TUNE_LATENCY;   // one pair at a time
     pf_plan* pl = pool_acquire(p, r);
     if (r) return r;
     r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
@@ -349,6 +358,7 @@ int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const dou
     // hard-coded solver constants of the fork: S/OpticalFlow.cpp:747-751; colType 0: wrapper :22
     int r = PF_OK;
     Params p{h, w, c, 0.012, 0.75, 20, pyramidLevels, 7, 1, 30, 0, mode, device};
+    p.tune = PF_TUNE_LATENCY;   // one pair at a time
     pf_plan* pl = pool_acquire(p, r);
     if (r) return r;
     r = pf_plan_execute(pl, vx, vy, warpI2, im1, im2, timings);
@@ -556,6 +566,7 @@ int pf_multigpu_flow(double* vx, double* vy, double* warpI2, const double* im1, 
             if ((r = check_device(devices[d]))) return r;
         if (nOuter < 0 || nInner < 0 || nSOR < 0) return fail(PF_EINVAL, "iteration counts must be non-negative");
         Params p{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, PF_MODE_FP32_REDBLACK, devices[0]};
+        p.tune = PF_TUNE_LATENCY;   // one pair over several GPUs
         multigpu_flow_f32(vx, vy, warpI2, im1, im2, p, devices, ndevices, split_min_pixels < 0 ? 2000000 : split_min_pixels, stats);
         return PF_OK;
     });

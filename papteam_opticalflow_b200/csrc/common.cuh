@@ -81,11 +81,12 @@ struct Params {
     int mode, device;
     int interp = solver_variant().interp;   // PF_INTERP_*: warp inside the pyramid loop
     int noise = solver_variant().noise;     // PF_NOISE_*: data-term weight model
+    int tune = PF_TUNE_THROUGHPUT;          // PF_TUNE_*: what the launch schedule of the SOR solves is fitted to (same results)
 };
 inline bool same_solver(const Params& a, const Params& b) {
     return a.h == b.h && a.w == b.w && a.c == b.c && a.alpha == b.alpha && a.ratio == b.ratio && a.min_width == b.min_width &&
            a.levels == b.levels && a.n_outer == b.n_outer && a.n_inner == b.n_inner && a.n_sor == b.n_sor &&
-           a.col_type == b.col_type && a.mode == b.mode && a.interp == b.interp && a.noise == b.noise;
+           a.col_type == b.col_type && a.mode == b.mode && a.interp == b.interp && a.noise == b.noise && a.tune == b.tune;
 }
 
 inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }

@@ -89,10 +89,11 @@ Taps<T> make_taps(const double* v, int half) {
 // costs `launch` cycles on top.  Two fits:
 //   throughput (default): SM time = tiles/148 x visit cost, small launch term -- what counts when many
 //       pairs are in flight and other streams fill the idle SMs of a small level (+6 % pairs/s);
-//   latency (PF_SOR_TUNE=latency): whole waves and the full launch/ramp cost of every pass -- it spreads
-//       small levels over all SMs with large halos and is ~8 % faster for ONE pair alone.
+//   latency (PF_TUNE_LATENCY plans: the one-shot entry points; PF_SOR_TUNE=latency forces it): whole waves and the
+//       full launch/ramp cost of every pass -- it spreads small levels over all SMs with large halos and is ~5 %
+//       faster for ONE pair alone (19.5 vs 20.5 ms at 1920x1080), 5 % slower with 16 pairs in flight.
 // PF_SOR_MODEL=a:b:launch:kind (kind 1 = whole waves, 0 = at least one wave, 2 = SM time) overrides.
-inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced, bool multi = false) {
+inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced, bool multi = false, int tune = PF_TUNE_THROUGHPUT) {
     if (w <= kSorRegionW && h <= region_h) return nsor;
     if (forced > 0) return std::min(forced, nsor);
     if (multi) {
@@ -114,13 +115,14 @@ inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced,
         }
         return best_t;
     }
-    static double ma = -1, mb = 0, ml = 0, mkind = 2;
-    if (ma < 0) {
-        const char* tune = getenv("PF_SOR_TUNE");
-        if (tune && !strcmp(tune, "latency")) { ma = 5500; mb = 380; ml = 7200; mkind = 1; }
-        else { ma = 8000; mb = 380; ml = 1500; mkind = 2; }
-        if (const char* e = getenv("PF_SOR_MODEL")) sscanf(e, "%lf:%lf:%lf:%lf", &ma, &mb, &ml, &mkind);
+    if (const char* e = getenv("PF_SOR_TUNE")) {   // forces one fit for every plan
+        if (!strcmp(e, "latency")) tune = PF_TUNE_LATENCY;
+        else if (!strcmp(e, "throughput")) tune = PF_TUNE_THROUGHPUT;
     }
+    double ma, mb, ml, mkind;
+    if (tune == PF_TUNE_LATENCY) { ma = 5500; mb = 380; ml = 7200; mkind = 1; }
+    else { ma = 8000; mb = 380; ml = 1500; mkind = 2; }
+    if (const char* e = getenv("PF_SOR_MODEL")) sscanf(e, "%lf:%lf:%lf:%lf", &ma, &mb, &ml, &mkind);
     double best = 1e300;
     int best_t = 1;
     for (int t = 1; t <= std::min(nsor, 12); t++) {
@@ -152,6 +154,7 @@ struct SorRunner {
     bool lex = false, simple_rb = false, use_tma = true;
     bool use_multi = false;                // PF_SOR_MULTI=1: all passes of a solve in one launch (k_sor_rb_multi); default one launch per pass
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
+    int tune = PF_TUNE_THROUGHPUT;
     cudaStream_t st = nullptr;
     unsigned int* ctrl = nullptr;          // k_sor_rb_multi: ticket counter + per-tile pass counters
     static constexpr int kCtrlWords = 1 << 15;
@@ -166,9 +169,10 @@ struct SorRunner {
     // stage + double-buffered exchange rows + alignment slack
     static size_t sor_smem_bytes() { return sizeof(SorStage<T, kR, kNW>) + sizeof(T) * 2 * 2 * kNW * 2 * kSorRegionW + 128; }
 
-    void init(int mode, int device, cudaStream_t stream) {
+    void init(int mode, int device, cudaStream_t stream, int tuning = PF_TUNE_THROUGHPUT) {
         lex = mode_is_lex(mode);
         st = stream;
+        tune = tuning;
         const char* e = getenv("PF_SOR_FUSE");
         forced_fuse = e ? atoi(e) : 0;
         e = getenv("PF_SOR_SIMPLE");
@@ -217,7 +221,7 @@ struct SorRunner {
 
     std::vector<SorPass> schedule(int w, int h, int nsor) const {
         std::vector<SorPass> v;
-        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse);
+        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse, false, tune);
         for (int done = 0; done < nsor;) {
             SorPass ps;
             ps.nsw = std::min(fuse, nsor - done);
@@ -362,7 +366,7 @@ class Plan : public PlanBase {
         PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
         allocate();
-        sor_.init(P.mode, P.device, st_);
+        sor_.init(P.mode, P.device, st_, P.tune);
     }
 
     ~Plan() override {

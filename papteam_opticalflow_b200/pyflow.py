@@ -33,6 +33,7 @@ _TIMING_KEYS = ["Total C++ Execution", "Construction", "Allocation", "Phase1_Gen
                 "Phase6_Update", "PostProcessing", "H2D", "D2H", "Solve"]
 
 
+TUNINGS = {"throughput": 0, "latency": 1}
 INTERPOLATIONS = {"bilinear": 0, "bicubic": 1}
 NOISE_MODELS = {"gmixture": 0, "lap": 1}
 
@@ -91,15 +92,19 @@ class FlowPlan(object):
     """Device arena + captured CUDA graph for one image shape / parameter set (pf_plan_*)."""
 
     def __init__(self, h, w, c, alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30,
-                 colType=0, levels=0, mode=None, device=0):
+                 colType=0, levels=0, mode=None, device=0, tuning="throughput"):
+        """tuning: 'throughput' (plans that run concurrently with others) or 'latency' (one pair at a time); it only
+        selects how many SOR sweeps a launch fuses per level, the results are bit-identical."""
+        if tuning not in TUNINGS:
+            raise ValueError("unknown tuning %r (expected one of %s)" % (tuning, sorted(TUNINGS)))
         self.shape = (int(h), int(w), int(c))
         self.mode = _mode_id(mode)
         self.device = int(device)
         self._h = C.c_void_p()
         self._lock = threading.Lock()
-        check(_lib.lib().pf_plan_create(C.byref(self._h), h, w, c, float(alpha), float(ratio), int(minWidth),
-                                        int(levels), int(nOuter), int(nInner), int(nSOR), int(colType),
-                                        self.mode, self.device))
+        check(_lib.lib().pf_plan_create_tuned(C.byref(self._h), h, w, c, float(alpha), float(ratio), int(minWidth),
+                                              int(levels), int(nOuter), int(nInner), int(nSOR), int(colType),
+                                              self.mode, self.device, TUNINGS[tuning]))
         self.levels = _lib.lib().pf_plan_levels(self._h)
 
     def close(self):
@@ -232,7 +237,7 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
     h, w, c = Im1.shape
     mid = _mode_id(mode)
     key = (h, w, c, tuple(sorted(p.items())), levels, mid, int(device), get_solver_variant())
-    plan = _get_plan(key, h=h, w=w, c=c, levels=levels, mode=mid, device=device, **p)
+    plan = _get_plan(key, h=h, w=w, c=c, levels=levels, mode=mid, device=device, tuning="latency", **p)   # one pair at a time
     t, vx, vy, wi = plan.execute(Im1, Im2)
     if fork:
         if profile:
