@@ -109,6 +109,12 @@ class HostStager {
     }
 
     void run(const std::vector<CopyJob>& jobs, bool to_dev, cudaStream_t other) {
+        if (!to_dev) {
+            // wait for the producer OUTSIDE the lock: with several host threads (batch workers) the stager must not be
+            // held for the length of one pair's solve while other threads have frames to upload
+            PF_CUDA(cudaSetDevice(dev_));
+            PF_CUDA(cudaStreamSynchronize(other));
+        }
         std::lock_guard<std::mutex> g(mu_);
         PF_CUDA(cudaSetDevice(dev_));
         std::vector<Chunk> chunks;
