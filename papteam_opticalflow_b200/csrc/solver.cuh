@@ -121,7 +121,7 @@ inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced,
     }
     double ma, mb, ml, mkind;
     if (tune == PF_TUNE_LATENCY) { ma = 5500; mb = 380; ml = 7200; mkind = 1; }
-    else { ma = 8000; mb = 380; ml = 1500; mkind = 2; }
+    else { ma = 12000; mb = 380; ml = 1500; mkind = 2; }   // refitted at the end of round 1: 127.0 -> 128.5 pairs/s vs a = 8000
     if (const char* e = getenv("PF_SOR_MODEL")) sscanf(e, "%lf:%lf:%lf:%lf", &ma, &mb, &ml, &mkind);
     double best = 1e300;
     int best_t = 1;
