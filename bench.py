@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fp32_redblack]
 
-A "step" is one BATCH of B frame pairs per GPU (default B=16; each pair 1920x1080 RGB, alpha=0.012
+A "step" is one BATCH of B frame pairs per GPU (default B=24; each pair 1920x1080 RGB, alpha=0.012
 ratio=0.75 minWidth=20 -> 15 levels, 7/1/30 iterations: BASELINE.json configs[2], the headline
 single-GPU case), the B solves running concurrently on B streams of the GPU (pairs are independent;
 the latency-bound coarse levels of one pair hide behind the bandwidth-bound fine levels of another).
@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="frame pairs in flight per GPU per step")
+    ap.add_argument("--batch", type=int, default=24, help="frame pairs in flight per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fp32_redblack", choices=["fp32_redblack", "fp64_wavefront", "fp64_redblack", "fp32_wavefront"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
