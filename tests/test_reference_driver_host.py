@@ -14,7 +14,8 @@ import pytest
 
 from conftest import GOLDEN
 
-DRIVER = "/root/reference/Code/Parallel/OpticalFlowCalculation.py"
+DRIVERS = {"parallel": "/root/reference/Code/Parallel/OpticalFlowCalculation.py",   # coarse2fine_flow(im1, im2, levels, nCores)
+           "serial": "/root/reference/Code/Serial/OpticalFlowCalculation.py"}       # coarse2fine_flow(im1, im2, levels)
 
 
 class _Img:
@@ -31,15 +32,19 @@ class _Pair:
         self.AFTER = _Img(os.path.join(GOLDEN, "frames", "hcm240_00002.jpg"), 2)
 
 
-@pytest.mark.skipif(not os.path.exists(DRIVER), reason="reference tree not present")
-def test_reference_driver_calls_the_drop_in_module(tmp_path, monkeypatch):
+@pytest.mark.parametrize("flavour", ["parallel", "serial"])
+def test_reference_driver_calls_the_drop_in_module(flavour, tmp_path, monkeypatch):
+    DRIVER = DRIVERS[flavour]
+    if not os.path.exists(DRIVER):
+        pytest.skip("reference tree not present")
+    call = (lambda drv: drv.CalculateOpticalFlow(_Pair(), 8, 4)) if flavour == "parallel" else (lambda drv: drv.CalculateOpticalFlow(_Pair(), 8))
     import pyflow                     # this repository's module
     from papteam_opticalflow_b200 import _lib
     assert "papteam_opticalflow_b200" in (pyflow.coarse2fine_flow.__module__ or "")
     # the driver imports matplotlib (unused on this path, not installed here) and its InputCreation package (optional)
     for name in ("matplotlib", "matplotlib.pyplot"):
         monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
-    spec = importlib.util.spec_from_file_location("ref_driver", DRIVER)
+    spec = importlib.util.spec_from_file_location("ref_driver_" + flavour, DRIVER)
     drv = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(drv)
     assert drv.pyflow is pyflow       # the driver bound OUR module under the reference's name
@@ -53,12 +58,12 @@ def test_reference_driver_calls_the_drop_in_module(tmp_path, monkeypatch):
     monkeypatch.setattr(drv.pyflow, "coarse2fine_flow", spy)
     monkeypatch.chdir(tmp_path)       # the driver writes under ./output
     if _lib.lib().pf_device_count() > 0:
-        drv.CalculateOpticalFlow(_Pair(), 8, 4)
+        call(drv)
         assert os.path.isdir(tmp_path / "output")
     else:
         with pytest.raises(pyflow.PyflowB200Error) as e:
-            drv.CalculateOpticalFlow(_Pair(), 8, 4)
+            call(drv)
         assert e.value.code == _lib.PF_ENODEVICE
-    im1, im2, levels, cores = seen["args"]
+    im1, im2, levels = seen["args"][:3]
     assert im1.dtype == np.float64 and im1.shape == (135, 240, 3) and im1.flags["C_CONTIGUOUS"] and im2.shape == im1.shape
-    assert (levels, cores) == (8, 4) and 0.0 <= im1.min() and im1.max() <= 1.0
+    assert levels == 8 and seen["args"][3:] == ((4,) if flavour == "parallel" else ()) and 0.0 <= im1.min() and im1.max() <= 1.0
