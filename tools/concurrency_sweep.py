@@ -7,7 +7,7 @@ from conftest import load_frame
 w = int(sys.argv[1]) if len(sys.argv) > 1 else 1920
 a, b = load_frame(w, 1), load_frame(w, 2)
 plans = []
-for B in (1, 4, 8, 12, 16, 24):
+for B in (1, 4, 8, 12, 16, 24, 32):
     while len(plans) < B:
         p = pyflow.FlowPlan(a.shape[0], a.shape[1], 3, mode="fp32_redblack"); p.upload(a, b); p.solve(2); plans.append(p)
     pyflow.multi_solve(plans[:B], 1)
