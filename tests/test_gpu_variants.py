@@ -117,3 +117,27 @@ def test_gaussian_mixture_fast_mode_short_horizon(variant):
             p.mixture_params()
     finally:
         p.close()
+
+
+def test_variant_reaches_batch_and_sequence_entry_points(variant):
+    """The process-global variant is sampled by every entry point that builds solver parameters: the batch and the
+    sequence paths must give the Bicubic result as well (and the default one again afterwards)."""
+    from PIL import Image
+    import os
+    from conftest import GOLDEN
+    f8 = [np.ascontiguousarray(np.array(Image.open(os.path.join(GOLDEN, "frames", "hcm240_%05d.jpg" % i)))) for i in (1, 2)]
+    a, b = f8[0].astype(float) / 255., f8[1].astype(float) / 255.
+    base_u, base_v, _ = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    variant("bicubic", "lap")
+    u, v, _ = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    assert np.abs(u - base_u).max() > 1e-3
+    outs, _ = pyflow.coarse2fine_flow_batch([(a, b), (a, b)], mode="fp32_redblack")
+    for ou, ov, _w in outs:
+        assert np.array_equal(ou, u) and np.array_equal(ov, v)
+    flows, _ = pyflow.sequence_flow(f8, mode="fp32_redblack")
+    assert np.array_equal(flows[0][..., 0], u.astype(np.float32)) and np.array_equal(flows[0][..., 1], v.astype(np.float32))
+    variant("bilinear", "lap")
+    outs, _ = pyflow.coarse2fine_flow_batch([(a, b)], mode="fp32_redblack")
+    assert np.array_equal(outs[0][0], base_u) and np.array_equal(outs[0][1], base_v)
+    flows, _ = pyflow.sequence_flow(f8, mode="fp32_redblack")
+    assert np.array_equal(flows[0][..., 0], base_u.astype(np.float32))
