@@ -14,9 +14,12 @@ Rank 0 prints exactly one JSON line (see the task contract):
   e2e        pairs/s through the public plan API with HOST (pinned) buffers: H2D + solve + D2H per step
   roofline   SOR kernel (k_sor_rb_tma) at pyramid level 0: algorithmic bytes (40 B per pixel-sweep in
              FP32) / CUDA-event time of its launches, against the measured HBM peak
-  cpu_baseline  the unmodified reference (oracle/_ref, Serial build, 1 core) on a bounded sample
---impl reference times the reference's own OpenMP build on all host cores on the same workload
-(bounded sample per step).  oracle/ is used here ONLY as that measured baseline, never by our arm.
+  cpu_baseline  the unmodified reference (oracle/_ref, Serial build, 1 core): ONE FULL 1920x1080 pair
+--impl reference times the reference's own OpenMP build on all host cores on the same workload, one FULL
+pair per step (no extrapolation).  oracle/ is used here ONLY as that measured baseline, never by our arm.
+Extra keys: e2e_flow_only (warpI2 = NULL), e2e_pageable, e2e_sequence (uint8 in / float32 out), per-leg
+milliseconds of the batch calls, config2_fp64_wavefront (960-wide pair, parity mode), config5_rowband (N > 1:
+one 4K pair split over all GPUs), single_pair_latency_ms, one_shot_call_ms, phases_ms.
 """
 import argparse
 import ctypes as C
@@ -36,24 +39,67 @@ sys.path.insert(0, ROOT)
 
 H, W, CH = 1080, 1920, 3
 PARAMS = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30, colType=0)
-SAMPLE_ROWS = 216          # CPU baselines run a 1920x216 band (1/5 of the pair) per step
 WORKLOAD = "HoChiMinhTraffic_10FPS_1920 pair, 1920x1080 RGB, defaults alpha=0.012 ratio=0.75 minWidth=20 (15 levels) 7/1/30"
+REF_COLLECTION = "/root/reference/images_New/HoChiMinhTraffic_10FPS_1920"
 
 
-def load_frames():
-    """Frames 1..3 of the reference's 1920-wide collection (byte copies under tests/golden/frames,
-    decoded like Par/OpticalFlowCalculation.py:66-71); synthetic textured frames if absent."""
-    try:
+class Frames(object):
+    """The 1920-wide collection BASELINE configs 3/4 name.  All 102 frames when the reference tree is on this machine
+    (or PF_BENCH_FRAMES points at a directory of frame_%05d.jpg files); otherwise the seven fixture copies under
+    tests/golden/frames (frames 1, 2, 3, 50, 51, 101, 102 -- the pairs SURVEY.md 8d spot-checks); synthetic texture if
+    neither can be decoded.  Decoding follows the reference driver (Par/OpticalFlowCalculation.py:66-71): PIL -> uint8
+    RGB -> astype(float) / 255.  Frames are decoded lazily: a rank only touches the frames of its own pairs."""
+
+    def __init__(self):
+        self.cache = {}
+        self.paths = {}
+        self.synthetic = None
+        src = os.environ.get("PF_BENCH_FRAMES", REF_COLLECTION)
+        try:
+            from PIL import Image  # noqa: F401
+            for i in range(1, 103):
+                q = os.path.join(src, "frame_%05d.jpg" % i)
+                if os.path.exists(q):
+                    self.paths[i] = q
+            if len(self.paths) >= 2:
+                self.data = "real: %d frames of HoChiMinhTraffic_10FPS_1920 read from %s" % (len(self.paths), src)
+            else:
+                self.paths = {}
+                for i in range(1, 103):
+                    q = os.path.join(ROOT, "tests", "golden", "frames", "hcm1920_%05d.jpg" % i)
+                    if os.path.exists(q):
+                        self.paths[i] = q
+                if len(self.paths) < 2:
+                    raise IOError("no fixture frames")
+                self.data = ("real: HoChiMinhTraffic_10FPS_1920 fixture frames %s (byte copies under tests/golden/frames; the full "
+                             "102-frame collection is not on this machine)" % ",".join(str(i) for i in sorted(self.paths)))
+        except Exception:
+            rng = np.random.default_rng(0)
+            base = rng.random((H // 8 + 4, W // 8 + 4, CH))
+            big = np.kron(base, np.ones((8, 8, 1)))
+            self.synthetic = [np.ascontiguousarray(big[8 + 2 * i:8 + 2 * i + H, 8 + 3 * i:8 + 3 * i + W]) for i in range(3)]
+            self.paths = {1: None, 2: None, 3: None}
+            self.data = "synthetic: block-noise texture translated by (3,2) px per frame"
+
+    def indices(self):
+        return sorted(self.paths)
+
+    def pairs(self):
+        """(t, t+1) for every frame t whose successor exists: the pairing rule of
+        Par/InputCreation/TestImagePairGenerator.py:151-171 (101 pairs for the full collection)."""
+        idx = self.indices()
+        return [(a, b) for a, b in zip(idx[:-1], idx[1:]) if b == a + 1]
+
+    def u8(self, i):
         from PIL import Image
-        fr = [np.array(Image.open(os.path.join(ROOT, "tests", "golden", "frames", "hcm1920_%05d.jpg" % i))).astype(float) / 255.
-              for i in (1, 2, 3)]
-        return fr, "real: HoChiMinhTraffic_10FPS_1920 frames 1-3 (fixture copies), pairs (1,2),(2,3) alternating"
-    except Exception:
-        rng = np.random.default_rng(0)
-        base = rng.random((H // 8 + 4, W // 8 + 4, CH))
-        big = np.kron(base, np.ones((8, 8, 1)))
-        fr = [np.ascontiguousarray(big[8 + 2 * i:8 + 2 * i + H, 8 + 3 * i:8 + 3 * i + W]) for i in range(3)]
-        return fr, "synthetic: block-noise texture translated by (3,2) px per frame"
+        if self.synthetic is not None:
+            return np.rint(self.synthetic[i - 1] * 255.0).astype(np.uint8)
+        return np.ascontiguousarray(np.array(Image.open(self.paths[i])))
+
+    def f64(self, i):
+        if i not in self.cache:
+            self.cache[i] = self.synthetic[i - 1] if self.synthetic is not None else self.u8(i).astype(float) / 255.
+        return self.cache[i]
 
 
 class ClockSampler(threading.Thread):
@@ -115,22 +161,20 @@ def pinned_like(lib, arr):
     return out, True
 
 
-def cpu_reference_sample(parallel, frames, reps=1):
-    """Runs the UNMODIFIED reference on a 1920 x SAMPLE_ROWS band; returns (pairs/s equivalent, cores, text)."""
+def cpu_reference_pair(parallel, im1, im2):
+    """ONE FULL 1920x1080 pair through the UNMODIFIED reference (oracle/_ref): Code/Parallel on all host cores this
+    process may use (P/OpticalFlow.cpp:735, nCores = that count; racy, timing only) or Code/Serial on one core.
+    Returns (seconds, cores)."""
     from oracle import ref
-    if not ref.available():
-        return None
-    a = np.ascontiguousarray(frames[0][432:432 + SAMPLE_ROWS]); b = np.ascontiguousarray(frames[1][432:432 + SAMPLE_ROWS])
     r = ref.parallel() if parallel else ref.serial()
-    cores = (os.cpu_count() or 1) if parallel else 1
-    best = None
-    for _ in range(reps):
-        t = time.perf_counter()
-        r.coarse2fine_flow_levels(a, b, 15, cores)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    frac = SAMPLE_ROWS / float(H)
-    return frac / best, cores, "rows 432..%d of frames 1-2 (1920x%d band, %.0f%% of the pair's pixels, 15 levels); pairs/s = %.2f / seconds" % (432 + SAMPLE_ROWS, SAMPLE_ROWS, 100 * frac, frac), best
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    cores = cores if parallel else 1
+    t = time.perf_counter()
+    r.coarse2fine_flow_levels(im1, im2, 15, cores)
+    return time.perf_counter() - t, cores
 
 
 def dist_setup(n):
@@ -145,12 +189,8 @@ def dist_setup(n):
 
 
 def dist_max(dist, local, x):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from papteam_opticalflow_b200.shard import max_over_ranks
+    return max_over_ranks(dist, x, device=("cuda:%d" % local) if dist is not None else None)
 
 
 def barrier(dist):
@@ -161,52 +201,129 @@ def barrier(dist):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own OpenMP implementation of the path on the box's host cores, one FULL
+    1920x1080 pair of the same workload per step (no extrapolation).  Rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames, data = load_frames()
+    frames = Frames()
     from oracle import ref
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference tree absent at build time)"}))
         return
-    for _ in range(args.warmup):
-        cpu_reference_sample(True, frames)
+    pairs = frames.pairs()
+    cores = 1
+    for k in range(args.warmup):
+        a, b = pairs[k % len(pairs)]
+        _, cores = cpu_reference_pair(True, frames.f64(a), frames.f64(b))
     t0 = time.perf_counter()
-    vals = [cpu_reference_sample(True, frames) for _ in range(args.steps)]
+    for k in range(args.steps):
+        a, b = pairs[k % len(pairs)]
+        _, cores = cpu_reference_pair(True, frames.f64(a), frames.f64(b))
     dt = time.perf_counter() - t0
-    frac = SAMPLE_ROWS / float(H)
-    value = args.steps * frac / dt
-    cores = vals[0][1]
+    value = args.steps / dt
+    sample = "one full 1920x1080 pair per step (15 levels), pairs %s in turn" % ",".join("%d-%d" % p for p in pairs[:min(len(pairs), args.steps)])
     line = {"impl": "reference", "metric": "frame_pairs_per_sec_1920w", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps / frac, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data,
-            "config": {"workload": WORKLOAD, "mode": "reference OpenMP build (Code/Parallel), nCores=%d" % cores},
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": vals[0][2]},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": frames.data,
+            "config": {"workload": WORKLOAD},
+            "setup": {"implementation": "reference OpenMP build (Code/Parallel, unmodified, racy for nCores > 1), nCores=%d" % cores,
+                      "pairs_per_step": 1},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def pinned_raw(lib, shape, dtype):
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.pf_host_alloc(nbytes)
+    if not ptr:
+        return np.zeros(shape, dtype), False
+    return np.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=dtype).reshape(shape), True
+
+
+def config2_parity_mode(pyflow, local):
+    """BASELINE configs[1]: the 960-wide pair in the FP64 lexicographic mode (the mode that matches the reference to
+    1e-6): device-resident ms per pair, median of 3 solves after one warm-up."""
+    try:
+        from PIL import Image
+        fr = [np.array(Image.open(os.path.join(ROOT, "tests", "golden", "frames", "hcm960_%05d.jpg" % i))).astype(float) / 255. for i in (1, 2)]
+    except Exception:
+        return None
+    h, w, c = fr[0].shape
+    plan = pyflow.FlowPlan(h, w, c, mode="fp64_wavefront", device=local, tuning="latency", **PARAMS)
+    plan.upload(fr[0], fr[1])
+    plan.solve(1)
+    ms = sorted(plan.solve(1) for _ in range(3))[1]
+    _, cnt = plan.profile()
+    plan.close()
+    return {"workload": "HoChiMinhTraffic_10FPS_960 pair, 960x540 RGB, defaults, 13 levels (BASELINE configs[1])", "mode": "fp64_wavefront",
+            "ms_per_pair": ms, "pairs_per_sec": 1000.0 / ms, "launches_per_solve": int(cnt[0]),
+            "round1_ms_per_pair": 287.0}
+
+
+def config5_rowband(pyflow, ndev):
+    """BASELINE configs[4]: ONE synthetic 3840x2160 gray pair (nSOR = 60, 18 levels) on one GPU and split into row bands
+    over all `ndev` GPUs of the node (pf_multigpu_flow; rank 0 drives every device, peer stores over NVLink)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from synth4k import make
+        im1, im2, _, _ = make()
+    except Exception as e:
+        return {"unavailable": "synthetic 4K pair: %r" % (e,)}
+    kw = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuterFPIterations=7, nInnerFPIterations=1, nSORIterations=60, colType=1)
+    out = {"workload": "synthetic 3840x2160 gray pair, affine motion, nSOR=60, 18 levels (BASELINE configs[4])"}
+    ref_flow = None
+    for tag, devs in (("1gpu", [0]), ("%dgpu" % ndev, list(range(ndev)))):
+        best, st, u, v = None, None, None, None
+        for _ in range(3):
+            u, v, _, st = pyflow.coarse2fine_flow_multigpu(im1, im2, devices=devs, **kw)
+            best = st["ms"] if best is None else min(best, st["ms"])
+        out["ms_" + tag] = best
+        if len(devs) > 1:
+            out.update(halo_bytes=st["halo_bytes"], gather_bytes=st["gather_bytes"], split_solves=st["split_solves"],
+                       graph=st["graph"], flag_solves=st["flag_solves"],
+                       bit_identical_to_1gpu=bool(np.array_equal(u, ref_flow[0]) and np.array_equal(v, ref_flow[1])))
+        else:
+            ref_flow = (u, v)
+    out["speedup"] = out["ms_1gpu"] / out["ms_%dgpu" % ndev]
+    return out
 
 
 def run_ours(args):
     dist, rank, local = dist_setup(args.gpus)
     import pyflow
     from papteam_opticalflow_b200 import _lib
+    from papteam_opticalflow_b200.shard import pairs_for_rank
     lib = _lib.lib()
     if lib.pf_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device and no CPU fallback")
-    frames, data = load_frames()
+    frames = Frames()
     B = max(1, args.batch)
+    # BASELINE configs[3]: pair p of the sequence belongs to GPU p mod G (no collective); every GPU keeps B pairs in
+    # flight per step (weak scaling), cycling through its own share of the sequence's pairs
+    all_pairs = frames.pairs()
+    idx = pairs_for_rank(len(all_pairs), rank, args.gpus) if len(all_pairs) >= args.gpus else []
+    if not idx:                                   # fewer fixture pairs than GPUs: every rank cycles through all of them
+        idx = list(range(len(all_pairs)))
+    mine = [all_pairs[i] for i in idx][:B]
     plans = [pyflow.FlowPlan(H, W, CH, mode=args.mode, device=local, **PARAMS) for _ in range(B)]
     plan = plans[0]
-    pin = [pinned_like(lib, f) for f in frames]
-    fr = [p[0] for p in pin]
-    pinned = all(p[1] for p in pin)
-    pairs = [(fr[0], fr[1]), (fr[1], fr[2])]
+    pinned = True
+    host = {}
+    for a, b in mine:
+        for i in (a, b):
+            if i not in host:
+                host[i], ok = pinned_like(lib, frames.f64(i))
+                pinned = pinned and ok
+    pairs = [(host[a], host[b]) for a, b in mine]
+    npair = len(pairs)
 
     # ---- device-resident throughput: K steps of B concurrent graph replays, one pair resident per
     #      plan; CUDA events on the launching stream around the whole region (pf_multi_solve) ----
     for i, p in enumerate(plans):
-        p.upload(*pairs[i % 2])
+        p.upload(*pairs[i % npair])
     pyflow.multi_solve(plans, max(1, args.warmup))
     sampler = ClockSampler(local); sampler.start()
     barrier(dist)
@@ -222,19 +339,31 @@ def run_ours(args):
     os.environ.setdefault("PF_BATCH_STREAMS", str(min(B, 8)))
     ring = B + 8                                        # output slots, reused cyclically (more than the workers in flight)
     host_outs = [tuple(pinned_like(lib, np.zeros(s))[0] for s in ((H, W), (H, W), (H, W, CH))) for _ in range(ring)]
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, ins, outs, flow_only=False):
         n = nsteps * B
-        pyflow.coarse2fine_flow_batch([pairs[i % 2] for i in range(n)], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"],
+        o = [outs[i % ring] for i in range(n)]
+        if flow_only:
+            o = [(x[0], x[1], None) for x in o]          # warpI2 = NULL: not copied back (the reference driver never reads it)
+        pyflow.coarse2fine_flow_batch([ins[i % npair] for i in range(n)], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"],
                                       PARAMS["nOuter"], PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"], mode=args.mode,
-                                      devices=[local], outs=[host_outs[i % ring] for i in range(n)])
-    e2e_run(max(1, min(2, args.warmup)))
-    barrier(dist)
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    e2e_s = time.perf_counter() - t0
-    barrier(dist)
-    e2e_s = dist_max(dist, local, e2e_s)
+                                      devices=[local], outs=o)
+    def timed(fn, nsteps):
+        barrier(dist)
+        t0 = time.perf_counter()
+        fn(nsteps)
+        dt = time.perf_counter() - t0
+        barrier(dist)
+        return dist_max(dist, local, dt)
+    e2e_run(max(1, min(2, args.warmup)), pairs, host_outs)
+    e2e_s = timed(lambda k: e2e_run(k, pairs, host_outs), args.steps)
     e2e = args.gpus * args.steps * B / e2e_s
+    legs = pyflow.batch_last_stats()
+    # the same call with warpI2 = NULL (what Par/OpticalFlowCalculation.py:74-76 consumes: u and v only)
+    half = max(1, args.steps // 2)
+    e2e_run(1, pairs, host_outs, True)
+    flow_s = timed(lambda k: e2e_run(k, pairs, host_outs, True), half)
+    e2e_flow = args.gpus * half * B / flow_s
+    legs_flow = pyflow.batch_last_stats()
 
     # ---- the same batch call on PAGEABLE numpy arrays (what a Python caller of the reference has): the library
     #      moves them through its multi-threaded pinned-slot stager (csrc/staging.hpp).  Extra key. ----
@@ -242,62 +371,65 @@ def run_ours(args):
     for o in page_outs:
         for a_ in o:
             a_.fill(0)          # touch the pages: a caller's buffers are normally mapped already
-    def page_run(nsteps):
-        n = nsteps * B
-        pyflow.coarse2fine_flow_batch([(frames[i % 2], frames[i % 2 + 1]) for i in range(n)], PARAMS["alpha"], PARAMS["ratio"],
-                                      PARAMS["minWidth"], PARAMS["nOuter"], PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"],
-                                      mode=args.mode, devices=[local], outs=[page_outs[i % ring] for i in range(n)])
-    page_run(1)
-    barrier(dist)
-    t0 = time.perf_counter()
-    page_run(max(1, args.steps // 2))
-    page_s = time.perf_counter() - t0
-    barrier(dist)
-    page_s = dist_max(dist, local, page_s)
-    e2e_page = args.gpus * max(1, args.steps // 2) * B / page_s
+    page_pairs = [(frames.f64(a), frames.f64(b)) for a, b in mine]
+    e2e_run(1, page_pairs, page_outs)
+    page_s = timed(lambda k: e2e_run(k, page_pairs, page_outs), half)
+    e2e_page = args.gpus * half * B / page_s
+    legs_page = pyflow.batch_last_stats()
 
-    # ---- sequence mode (reported beside the headline, not instead of it): K*B+1 uint8
-    #      frames in, K*B float32 flows out, every frame's pyramid built once, conversion from uint8 on the device ----
-    def pinned_raw(shape, dtype):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        ptr = lib.pf_host_alloc(nbytes)
-        if not ptr:
-            return np.zeros(shape, dtype)
-        return np.frombuffer((C.c_ubyte * nbytes).from_address(ptr), dtype=dtype).reshape(shape)
-    u8 = []
-    for f in frames:
-        a = pinned_raw(f.shape, np.uint8)
-        a[...] = np.rint(f * 255.0).astype(np.uint8)
-        u8.append(a)
-    seq_outs = [pinned_raw((H, W, 2), np.float32) for _ in range(ring)]
+    # ---- sequence mode (BASELINE configs[3] as the reference driver would run it): K*B+1
+    #      uint8 frames in, K*B float32 flows out, every frame's pyramid built once, conversion from uint8 on the device ----
+    seq_idx = []
+    for a, b in mine:                 # a walk over this rank's frames in which every consecutive pair is a real pair
+        if not seq_idx or seq_idx[-1] != a:
+            seq_idx.append(a)
+        seq_idx.append(b)
+    walk = seq_idx + seq_idx[-2:0:-1]           # forward then backward, cyclic
+    u8 = {}
+    for i in set(walk):
+        u8[i], _ = pinned_raw(lib, (H, W, CH), np.uint8)
+        u8[i][...] = frames.u8(i)
+    seq_outs = [pinned_raw(lib, (H, W, 2), np.float32)[0] for _ in range(ring)]
     def seq_run(nsteps):
         n = nsteps * B
-        pyflow.sequence_flow([u8[i % 3] for i in range(n + 1)], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"], PARAMS["nOuter"],
-                             PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"], mode=args.mode, devices=[local],
+        pyflow.sequence_flow([u8[walk[i % len(walk)]] for i in range(n + 1)], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"],
+                             PARAMS["nOuter"], PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"], mode=args.mode, devices=[local],
                              outs=[seq_outs[i % ring] for i in range(n)])
     seq_run(max(1, min(2, args.warmup)))
-    barrier(dist)
-    t0 = time.perf_counter()
-    seq_run(args.steps)
-    seq_s = time.perf_counter() - t0
-    barrier(dist)
-    seq_s = dist_max(dist, local, seq_s)
+    seq_s = timed(seq_run, args.steps)
     clocks = sampler.summary()
     seq = args.gpus * args.steps * B / seq_s
+
+    # ---- BASELINE configs[4] at N > 1: rank 0 splits ONE 4K pair into row bands over all N GPUs while the others wait ----
+    rowband = None
+    if dist is not None:
+        barrier(dist)
+        if rank == 0 and not args.no_rowband:
+            try:
+                rowband = config5_rowband(pyflow, args.gpus)
+            except Exception as e:
+                rowband = {"failed": repr(e)[:300]}
+        barrier(dist)
 
     line = None
     if rank == 0:
         # ---- the drop-in call itself: pyflow.coarse2fine_flow on plain (pageable) numpy arrays, fresh outputs, one
         #      pair at a time -- what a caller of the reference's module sees (extra key, not the headline) ----
         one_shot = []
-        for _ in range(4):
+        f0, f1 = page_pairs[0]
+        for _ in range(5):
             t0 = time.perf_counter()
-            pyflow.coarse2fine_flow(frames[0], frames[1], PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"], PARAMS["nOuter"],
+            pyflow.coarse2fine_flow(f0, f1, PARAMS["alpha"], PARAMS["ratio"], PARAMS["minWidth"], PARAMS["nOuter"],
                                     PARAMS["nInner"], PARAMS["nSOR"], PARAMS["colType"], mode=args.mode, device=local)
             one_shot.append(1000 * (time.perf_counter() - t0))
         one_shot_ms = float(np.median(one_shot[1:]))
+        # ---- single-pair latency (latency-tuned plan, what the one-shot entry points use) ----
+        lat_plan = pyflow.FlowPlan(H, W, CH, mode=args.mode, device=local, tuning="latency", **PARAMS)
+        lat_plan.upload(*pairs[0])
+        lat_plan.solve(2)
+        single_ms = lat_plan.solve(5) / 5
+        lat_plan.close()
         # ---- per-phase attribution + SOR roofline from one eager, event-instrumented solve ----
-        single_ms = plan.solve(3) / 3
         plan.profile()
         tp, cnt = plan.profile()
         peak, peak_src = hbm_peak()
@@ -306,37 +438,59 @@ def run_ours(args):
         bytes_per_launch = ps_l0 * 10 * word / max(1.0, sor_launch_l0)
         achieved = (ps_l0 * 10 * word / 1e9) / (sor_ms_l0 / 1e3) if sor_ms_l0 > 0 else 0.0
         sor_all = (cnt[2] * 10 * word / 1e9) / (tp[_lib.T_PHASE5] / 1e3) if tp[_lib.T_PHASE5] > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tf = os.path.join(ROOT, "profiles", "sor_traffic.json")
         if os.path.exists(tf):
             try:
-                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                tj = json.load(open(tf))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "committed ncu figure (%s), not measured in this run" % tj.get("source", "profiles/sor_traffic.json")
             except Exception:
                 traffic = None
         cpu = None
         if args.gpus == 1 and not args.no_cpu:
             try:
-                r = cpu_reference_sample(False, frames)
-                if r:
-                    cpu = {"value": r[0], "unit": "pairs/s", "cores": r[1], "kind": "reference", "sample": r[2], "seconds": r[3]}
+                from oracle import ref
+                if ref.available():
+                    a, b = mine[0]
+                    secs, cores = cpu_reference_pair(False, frames.f64(a), frames.f64(b))
+                    cpu = {"value": 1.0 / secs, "unit": "pairs/s", "cores": cores, "kind": "reference", "seconds": secs,
+                           "sample": "one full 1920x1080 pair (frames %d-%d, 15 levels) through the unmodified Code/Serial build" % (a, b)}
             except Exception as e:   # the baseline must never break the GPU line
                 cpu = {"value": None, "unit": "pairs/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
+        cfg2 = None
+        if not args.no_config2:
+            try:
+                cfg2 = config2_parity_mode(pyflow, local)
+            except Exception as e:
+                cfg2 = {"failed": repr(e)[:300]}
         phases = {k: round(float(tp[i]), 3) for i, k in enumerate(
             ["total", "pyramid", "features_upsample_warp", "getDxs", "phi", "psi(fused)", "assemble", "sor", "update_warp", "bicubic_export"])}
+        leg = lambda d: {k: round(float(d[k]), 3) for k in ("h2d_ms", "solve_ms", "d2h_ms", "call_ms")}  # noqa: E731
+        h2d_pair, d2h_pair = 2 * H * W * CH * 8, (2 * H * W + H * W * CH) * 8
         line = {
             "metric": "frame_pairs_per_sec_1920w", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_pair": ms / args.steps / B,
             "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode.startswith("fp32") else "f64", "data": data,
-            "config": {"workload": WORKLOAD, "mode": args.mode, "pairs_per_gpu_per_step": B,
-                       "concurrency": "%d pairs in flight per GPU, one CUDA stream + graph each" % B,
-                       "l2": "per-solve working set ~0.5 GB of planes > 126 MB L2 (no explicit flush)",
-                       "host_buffers": "pinned" if pinned else "pageable"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode.startswith("fp32") else "f64", "data": frames.data,
+            "config": {"workload": WORKLOAD},          # the same dict in the reference arm's line
+            "setup": {"mode": args.mode, "pairs_per_gpu_per_step": B,
+                      "pairs": "sequence pairs %s on rank 0 (pair p -> GPU p mod N)" % ",".join("%d-%d" % q for q in mine[:8]),
+                      "concurrency": "%d pairs in flight per GPU, one CUDA stream + graph each" % B,
+                      "l2": "per-solve working set ~0.5 GB of planes > 126 MB L2 (no explicit flush)",
+                      "host_buffers": "pinned" if pinned else "pageable"},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * 2 * H * W * CH * 8),
-                    "d2h_bytes_per_step": int(B * (2 * H * W + H * W * CH) * 8), "ms_per_step": 1000 * e2e_s / args.steps,
-                    "api": "pyflow.coarse2fine_flow_batch -> pf_batch_flow (host float64 HWC in, host float64 out)"},
-            "e2e_pageable": {"value": e2e_page, "unit": "pairs/s",
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * h2d_pair),
+                    "d2h_bytes_per_step": int(B * d2h_pair), "ms_per_step": 1000 * e2e_s / args.steps,
+                    "legs_ms_per_pair_rank0": leg(legs),
+                    "host_GBps": args.gpus * args.steps * B * (h2d_pair + d2h_pair) / e2e_s / 1e9,
+                    "api": "pyflow.coarse2fine_flow_batch -> pf_batch_flow (host float64 HWC in, host float64 vx, vy, warpI2 out)"},
+            "e2e_flow_only": {"value": e2e_flow, "unit": "pairs/s", "h2d_bytes_per_step": int(B * h2d_pair),
+                              "d2h_bytes_per_step": int(B * 2 * H * W * 8), "legs_ms_per_pair_rank0": leg(legs_flow),
+                              "host_GBps": args.gpus * half * B * (h2d_pair + 2 * H * W * 8) / flow_s / 1e9,
+                              "api": "the same call with warpI2 = NULL: u and v only, what the reference driver consumes "
+                                     "(Par/OpticalFlowCalculation.py:74-76)"},
+            "e2e_pageable": {"value": e2e_page, "unit": "pairs/s", "legs_ms_per_pair_rank0": leg(legs_page),
                              "api": "the same batch call with plain (pageable) numpy arrays in and out, staged by the library"},
             "e2e_sequence": {"value": seq, "unit": "pairs/s", "h2d_bytes_per_step": B * H * W * CH, "d2h_bytes_per_step": B * H * W * 8,
                              "api": "pyflow.sequence_flow -> pf_sequence_flow_u8 (host uint8 frames in, host float32 (u,v) out; consecutive "
@@ -345,12 +499,14 @@ def run_ours(args):
             "single_pair_latency_ms": single_ms,
             "one_shot_call_ms": one_shot_ms,
             "roofline": {"bound": "hbm", "kernel": "k_sor_rb_tma (level 0, 1920x1080)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_solve_level0": int(sor_launch_l0),
                          "avg_launch_ms": sor_ms_l0 / max(1.0, sor_launch_l0),
                          "sor_all_levels_GBps": sor_all, "sor_all_levels_frac": sor_all / peak,
                          "timing": "CUDA events on the launching stream around the SOR launches of one eager solve"},
             "cpu_baseline": cpu,
+            "config2_fp64_wavefront": cfg2,
+            "config5_rowband": rowband,
             "phases_ms": phases,
             "launches_per_solve": int(cnt[0]),
         }
@@ -370,6 +526,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fp32_redblack", choices=["fp32_redblack", "fp64_wavefront", "fp64_redblack", "fp32_wavefront"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config2", action="store_true", help="skip the 960-wide fp64_wavefront leg")
+    ap.add_argument("--no-rowband", action="store_true", help="skip the 4K row-band split leg at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -129,7 +129,9 @@ int pf_plan_create_tuned(pf_plan** plan, int h, int w, int c, double alpha, doub
                          int colType, int mode, int device, int tuning);
 int pf_plan_destroy(pf_plan* plan);
 int pf_plan_levels(const pf_plan* plan);
-/* H2D + solve + D2H with host buffers (pageable or pinned). */
+/* H2D + solve + D2H with host buffers (pageable or pinned).  Any of vx / vy / warpI2 may be NULL: that output is
+ * not copied back (the reference driver never reads warpI2, Par/OpticalFlowCalculation.py:74-76; it is 60 % of the
+ * device->host bytes).  The same holds for pf_plan_download and, per pair or per array, for pf_batch_flow. */
 int pf_plan_execute(pf_plan* plan, double* vx, double* vy, double* warpI2, const double* im1,
                     const double* im2, double* timings);
 /* The same three legs separately, for resident-input measurement. */
@@ -160,6 +162,11 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                   int minWidth, int levels, int nOuterFPIterations, int nInnerFPIterations,
                   int nSORIterations, int colType, int h, int w, int c, int mode,
                   const int* devices, int ndevices, double* seconds);
+
+/* Event-timed legs of the LAST pf_batch_flow call of this process, 8 doubles: [0] pairs, [1] worker threads,
+ * [2] wall seconds, mean per pair in ms of [3] H2D, [4] solve, [5] D2H (CUDA events on the pair's stream),
+ * [6] host wall time of the whole pf_plan_execute call, [7] 0. */
+int pf_batch_last_stats(double* out);
 
 /* ---- sequences (SURVEY.md 8f "next" rows f1 + f2): nframes uint8 HWC frames (as PIL decodes
  * them, Par/OpticalFlowCalculation.py:66-67) -> nframes-1 flows of the consecutive pairs (t, t+1)

@@ -63,6 +63,7 @@ def lib():
         "pf_plan_mixture_params": (i, [v, dp, dp, dp, i]),
         "pf_multi_solve": (i, [C.POINTER(v), i, i, dp]),
         "pf_batch_flow": (i, [i, dpp, dpp, dpp, dpp, dpp, d, d, i, i, i, i, i, i, i, i, i, i, ip, i, dp]),
+        "pf_batch_last_stats": (i, [dp]),
         "pf_sequence_flow_u8": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_float)), d, d, i, i, i, i, i, i, i, i, i, i,
                                     ip, i, dp]),
         "pf_sequence_flow_u8_u16": (i, [i, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.POINTER(C.c_ushort)), d, d, i, i, i, i, i, i, i, i, i, i,

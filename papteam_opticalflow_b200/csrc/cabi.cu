@@ -20,6 +20,7 @@ struct pf_plan {
 namespace {
 
 thread_local std::string g_err;
+int (*g_pool_purge)() = nullptr;   // set below to pf_pool_clear
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -33,6 +34,9 @@ int guarded(F&& f) {
         return f();
     } catch (const Error& e) {
         cudaGetLastError();  // clear the sticky-less error state
+        // a failed kernel leaves the context unusable (sticky error): idle pooled plans would be handed out again
+        // and again -- drop them so that later calls rebuild (or fail cleanly at plan creation)
+        if (e.code == PF_ECUDA && g_pool_purge) g_pool_purge();
         return fail(e.code, e.what());
     } catch (const std::bad_alloc&) {
         return fail(PF_ENOMEM, "host allocation failed");
@@ -88,6 +92,9 @@ std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
 unsigned long long g_pool_clock = 0;
 const size_t kPoolMax = 16;
+
+std::mutex g_batch_stats_mu;
+double g_batch_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // of the last pf_batch_flow call (pf_batch_last_stats)
 
 bool same_params(const Params& a, const Params& b) { return same_solver(a, b) && a.device == b.device; }
 
@@ -146,7 +153,11 @@ pf_plan* pool_acquire(const Params& p, int& rc) {
 // entry point loses 13 % with the variable unset).  It is read when the CUDA context is created, so it is
 // set -- without overriding the user's choice -- when this library is loaded; a host process that created
 // its context earlier must export it itself.
-__attribute__((constructor)) static void pf_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+extern "C" int pf_pool_clear(void);
+__attribute__((constructor)) static void pf_default_connections() {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    g_pool_purge = pf_pool_clear;
+}
 
 extern "C" {
 
@@ -244,8 +255,8 @@ int pf_plan_levels(const pf_plan* plan) { return plan ? plan->impl->levels() : P
 int pf_plan_execute(pf_plan* plan, double* vx, double* vy, double* warpI2, const double* im1,
                     const double* im2, double* timings) {
     return guarded([&]() -> int {
-        if (!plan || !vx || !vy || !warpI2 || !im1 || !im2) return fail(PF_EINVAL, "NULL argument");
-        plan->impl->execute(vx, vy, warpI2, im1, im2, timings);
+        if (!plan || !im1 || !im2) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->execute(vx, vy, warpI2, im1, im2, timings);   // NULL outputs are not copied back
         return PF_OK;
     });
 }
@@ -268,8 +279,8 @@ int pf_plan_solve(pf_plan* plan, int repeats, double* ms_total) {
 
 int pf_plan_download(pf_plan* plan, double* vx, double* vy, double* warpI2) {
     return guarded([&]() -> int {
-        if (!plan || !vx || !vy || !warpI2) return fail(PF_EINVAL, "NULL argument");
-        plan->impl->download(vx, vy, warpI2);
+        if (!plan) return fail(PF_EINVAL, "NULL argument");
+        plan->impl->download(vx, vy, warpI2);   // NULL outputs are not copied back
         return PF_OK;
     });
 }
@@ -366,6 +377,13 @@ int pf_coarse2fine_flow_levels(double* vx, double* vy, double* warpI2, const dou
     return r;
 }
 
+int pf_batch_last_stats(double* out) {
+    if (!out) return fail(PF_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(g_batch_stats_mu);
+    for (int i = 0; i < 8; i++) out[i] = g_batch_stats[i];
+    return PF_OK;
+}
+
 int pf_pool_clear(void) {
     std::vector<pf_plan*> all;
     {
@@ -387,7 +405,7 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                   int minWidth, int levels, int nOuter, int nInner, int nSOR, int colType, int h,
                   int w, int c, int mode, const int* devices, int ndevices, double* seconds) {
     if (npairs < 0 || ndevices < 1 || !devices) return fail(PF_EINVAL, "bad batch arguments");
-    if (npairs > 0 && (!vx || !vy || !warpI2 || !im1 || !im2)) return fail(PF_EINVAL, "NULL argument");
+    if (npairs > 0 && (!im1 || !im2)) return fail(PF_EINVAL, "NULL argument");
     for (int d = 0; d < ndevices; d++) {
         int r = check_device(devices[d]);
         if (r) return r;
@@ -422,8 +440,9 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
                 int p = d + k * ndevices;
                 if (p >= npairs) break;
                 double t[PF_NUM_TIMINGS];
-                r = pf_plan_execute(pl, vx[p], vy[p], warpI2[p], im1[p], im2[p], trace ? t : nullptr);
-                if (trace && r == PF_OK) {
+                // an output array that is NULL, or a NULL entry in it, means "do not copy this output back"
+                r = pf_plan_execute(pl, vx ? vx[p] : nullptr, vy ? vy[p] : nullptr, warpI2 ? warpI2[p] : nullptr, im1[p], im2[p], t);
+                if (r == PF_OK) {
                     std::lock_guard<std::mutex> lk(trace_mu);
                     trace_sum[0] += t[PF_T_H2D]; trace_sum[1] += t[PF_T_SOLVE]; trace_sum[2] += t[PF_T_D2H]; trace_sum[3] += 1;
                     trace_sum[4] += t[13]; trace_sum[5] += t[14]; trace_sum[6] += t[15];
@@ -437,6 +456,13 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
     for (auto& t : workers) t.join();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (seconds) *seconds = secs;
+    {
+        std::lock_guard<std::mutex> lk(g_batch_stats_mu);
+        const double n = trace_sum[3] > 0 ? trace_sum[3] : 1;
+        g_batch_stats[0] = trace_sum[3]; g_batch_stats[1] = (double)nworkers; g_batch_stats[2] = secs;
+        g_batch_stats[3] = trace_sum[0] / n; g_batch_stats[4] = trace_sum[1] / n; g_batch_stats[5] = trace_sum[2] / n;
+        g_batch_stats[6] = trace_sum[6] / n; g_batch_stats[7] = 0;
+    }
     if (trace && trace_sum[3] > 0)
         fprintf(stderr, "[pf_batch_flow] %d pairs, %d workers, %.3f s: mean per pair H2D %.2f ms, solve %.2f ms, D2H %.2f ms; host: copy enqueue %.2f ms, "
                 "graph launch %.2f ms, whole call %.2f ms\n", npairs, nworkers, secs, trace_sum[0] / trace_sum[3], trace_sum[1] / trace_sum[3],

@@ -15,7 +15,12 @@ void multigpu_flow_f32(double* vx, double* vy, double* warp, const double* im1, 
         cached.reset();
         cached.reset(new MultiPlan(p, devices, ndev, split_min_pixels));
     }
-    cached->execute(vx, vy, warp, im1, im2, stats);
+    try {
+        cached->execute(vx, vy, warp, im1, im2, stats);
+    } catch (...) {
+        cached.reset();      // never reuse a plan whose solve failed (sticky context errors, lost neighbours)
+        throw;
+    }
 }
 PlanBase* make_plan_f32(const Params& p) { return new Plan<float>(p); }
 const StageCalls& stages_f32() {

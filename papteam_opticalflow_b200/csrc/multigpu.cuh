@@ -78,7 +78,7 @@ class MultiPlan {
             flags_.assign((size_t)ndev, nullptr);
             for (int g = 0; g < ndev; g++) {
                 PF_CUDA(cudaSetDevice(devs_[g]));
-                PF_CUDA(cudaMalloc(&flags_[(size_t)g], kFlagSlots * 2 * sizeof(unsigned int)));
+                PF_CUDA(cudaMalloc(&flags_[(size_t)g], (kFlagSlots * 2 + 1) * sizeof(unsigned int)));   // + the error word
             }
         }
     }
@@ -112,6 +112,19 @@ class MultiPlan {
         run_solve();
         sync_all();
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t g = 0; g < flags_.size(); g++) {      // a pass that ran out of time waiting for a neighbour's counters
+            unsigned int lost = 0;
+            on((int)g);
+            PF_CUDA(cudaMemcpy(&lost, flags_[g] + 2 * kFlagSlots, sizeof(lost), cudaMemcpyDeviceToHost));
+            if (lost) {
+                flags_ok_ = false;                         // this plan falls back to stream events from now on
+                if (gexec_) { cudaGraphExecDestroy(gexec_); gexec_ = nullptr; }
+                if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+                throw Error(PF_ECUDA, "row-band split: device " + std::to_string(devs_[g]) + " waited 20 s for the " +
+                                          (lost == 1 ? "upper" : "lower") + " neighbour's pass counters (is that GPU busy with other work?); "
+                                          "the result was discarded, later calls order the passes with stream events");
+            }
+        }
         plans_[0]->download(vx, vy, warp);
         if (stats) {
             stats[0] = ms;
@@ -139,9 +152,13 @@ class MultiPlan {
         const char* e = getenv("PF_NO_GRAPH");
         if (e && atoi(e)) { solve(); return; }
         cudaStream_t s0 = plans_[0]->stream();
-        if (!gexec_ && !graph_failed_) {
+        // ThreadLocal like Plan::run_solve: another thread's cudaMalloc / cudaHostAlloc (pool_acquire, the stager, ...)
+        // must neither fail nor invalidate this capture.  A failed capture is retried once before the plan settles for
+        // eager launches (reported through stats[4] = 0 and PF_MULTI_TRACE).
+        for (int attempt = 0; attempt < 2 && !gexec_ && !graph_failed_; attempt++) {
             on(0);
-            cudaError_t st = cudaStreamBeginCapture(s0, cudaStreamCaptureModeGlobal);
+            cudaError_t st = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
+            std::string why;
             if (st == cudaSuccess) {
                 try {
                     PF_CUDA(cudaEventRecord(ev_fork_, s0));
@@ -156,19 +173,23 @@ class MultiPlan {
                     on(0);
                     PF_CUDA(cudaStreamEndCapture(s0, &graph_));
                     PF_CUDA(cudaGraphInstantiate(&gexec_, graph_, 0));
-                } catch (const Error& err) {
-                    if (getenv("PF_MULTI_TRACE")) fprintf(stderr, "pyflow_b200 multigpu: graph capture failed: %s\n", err.what());
+                } catch (const std::exception& err) {
+                    why = err.what();
                     cudaGraph_t g = nullptr;
+                    on(0);
                     cudaStreamEndCapture(s0, &g);
                     if (g) cudaGraphDestroy(g);
+                    if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
                     cudaGetLastError();
-                    graph_failed_ = true;
                     gexec_ = nullptr;
                 }
             } else {
-                if (getenv("PF_MULTI_TRACE")) fprintf(stderr, "pyflow_b200 multigpu: cudaStreamBeginCapture failed: %s\n", cudaGetErrorString(st));
+                why = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(st);
                 cudaGetLastError();
-                graph_failed_ = true;
+            }
+            if (!gexec_) {
+                if (getenv("PF_MULTI_TRACE")) fprintf(stderr, "pyflow_b200 multigpu: graph capture failed (attempt %d): %s\n", attempt + 1, why.c_str());
+                if (attempt == 1) graph_failed_ = true;
             }
         }
         if (gexec_) {
@@ -194,7 +215,7 @@ class MultiPlan {
         if (flags_ok_)   // counters start at zero in every solve (the first split solve's opening barrier orders this)
             for (int g = 0; g < G; g++) {
                 on(g);
-                PF_CUDA(cudaMemsetAsync(flags_[(size_t)g], 0, kFlagSlots * 2 * sizeof(unsigned int), plans_[g]->stream()));
+                PF_CUDA(cudaMemsetAsync(flags_[(size_t)g], 0, (kFlagSlots * 2 + 1) * sizeof(unsigned int), plans_[g]->stream()));
             }
         for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_begin(); }
         const int nlev = plans_[0]->levels();
@@ -320,6 +341,7 @@ class MultiPlan {
                 }
                 if (use_flags) {
                     const int slot = flag_slot_ + (int)p;
+                    peer.error_word = flags_[(size_t)g] + 2 * kFlagSlots;
                     if (p > 0) {          // the neighbours' previous pass: counters of slot - 1 in OUR memory
                         int nb, ne;
                         if (g > 0) {

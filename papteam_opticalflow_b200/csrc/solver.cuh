@@ -93,28 +93,9 @@ Taps<T> make_taps(const double* v, int half) {
 //       full launch/ramp cost of every pass -- it spreads small levels over all SMs with large halos and is ~5 %
 //       faster for ONE pair alone (19.5 vs 20.5 ms at 1920x1080), 5 % slower with 16 pairs in flight.
 // PF_SOR_MODEL=a:b:launch:kind (kind 1 = whole waves, 0 = at least one wave, 2 = SM time) overrides.
-inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced, bool multi = false, int tune = PF_TUNE_THROUGHPUT) {
+inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced, int tune = PF_TUNE_THROUGHPUT) {
     if (w <= kSorRegionW && h <= region_h) return nsor;
     if (forced > 0) return std::min(forced, nsor);
-    if (multi) {
-        // k_sor_rb_multi: no launch, first-load or tail cost per pass -- SM time = visits x (a + 2 t b); PF_SOR_MODEL_MULTI=a:b
-        static double qa = -1, qb = 380;
-        if (qa < 0) {
-            qa = 4500;
-            if (const char* e = getenv("PF_SOR_MODEL_MULTI")) sscanf(e, "%lf:%lf", &qa, &qb);
-        }
-        double best = 1e300;
-        int best_t = 1;
-        for (int t = 1; t <= std::min(nsor, 12); t++) {
-            SorTiling tx = sor_tiling(w, kSorRegionW, 2 * t), ty = sor_tiling(h, region_h, 2 * t);
-            if (tx.ntiles == 0 || ty.ntiles == 0) break;
-            // the last pass runs only the remaining sweeps but pays a full visit
-            const double passes = std::ceil((double)nsor / t);
-            const double cost = (double)tx.ntiles * ty.ntiles * (passes * qa + 2.0 * nsor * qb);
-            if (cost < best) { best = cost; best_t = t; }
-        }
-        return best_t;
-    }
     if (const char* e = getenv("PF_SOR_TUNE")) {   // forces one fit for every plan
         if (!strcmp(e, "latency")) tune = PF_TUNE_LATENCY;
         else if (!strcmp(e, "throughput")) tune = PF_TUNE_THROUGHPUT;
@@ -152,19 +133,13 @@ struct SorRunner {
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
     bool lex = false, simple_rb = false, use_tma = true;
-    bool use_multi = false;                // PF_SOR_MULTI=1: all passes of a solve in one launch (k_sor_rb_multi); default one launch per pass
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     int tune = PF_TUNE_THROUGHPUT;
     cudaStream_t st = nullptr;
-    unsigned int* ctrl = nullptr;          // k_sor_rb_multi: ticket counter + per-tile pass counters
-    static constexpr int kCtrlWords = 1 << 15;
 
     SorRunner() = default;
     SorRunner(const SorRunner&) = delete;
     SorRunner& operator=(const SorRunner&) = delete;
-    ~SorRunner() {
-        if (ctrl) cudaFree(ctrl);
-    }
 
     // stage + double-buffered exchange rows + alignment slack
     static size_t sor_smem_bytes() { return sizeof(SorStage<T, kR, kNW>) + sizeof(T) * 2 * 2 * kNW * 2 * kSorRegionW + 128; }
@@ -180,17 +155,6 @@ struct SorRunner {
         e = getenv("PF_SOR_TMA");
         use_tma = !(e && !atoi(e));
         PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        // k_sor_rb_multi is opt-in: alone, a solve of the four finest levels is 5-25 % faster with it, but inside the
-        // whole pyramid the single-pair latency does not move and with 16 pairs in flight throughput drops 5-7 %
-        // (waiting CTAs keep their SMs; the idle tails it removes were already filled by other pairs' kernels)
-        e = getenv("PF_SOR_MULTI");
-        use_multi = e && atoi(e) && !kF64;
-        if (!lex && !simple_rb && use_tma && use_multi) {
-            if constexpr (!kF64) {
-                PF_CUDA(cudaFuncSetAttribute(k_sor_rb_multi<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sor_smem_bytes()));
-                PF_CUDA(cudaMalloc(&ctrl, kCtrlWords * sizeof(unsigned int)));
-            }
-        }
         if (!lex && !simple_rb && use_tma) {
             size_t bytes = sor_smem_bytes();
             PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -221,7 +185,7 @@ struct SorRunner {
 
     std::vector<SorPass> schedule(int w, int h, int nsor) const {
         std::vector<SorPass> v;
-        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse, false, tune);
+        int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse, tune);
         for (int done = 0; done < nsor;) {
             SorPass ps;
             ps.nsw = std::min(fuse, nsor - done);
@@ -292,41 +256,6 @@ struct SorRunner {
                 }
             return launches;
         }
-        if constexpr (!kF64) {
-            if (use_multi && use_tma && ctrl) {
-                // all passes in one launch, ordered tile by tile (k_sor_rb_multi)
-                const int fuse = choose_fused_sweeps(w, h, nsor, kRegionH, forced_fuse, true);
-                const SorTiling tx = sor_tiling(w, kSorRegionW, 2 * fuse), ty = sor_tiling(h, kRegionH, 2 * fuse);
-                const int npasses = (nsor + fuse - 1) / fuse, ntiles = tx.ntiles * ty.ntiles;
-                // Worth it where a CTA sees more than one tile per pass (measured, tools/sor_sweep.py: 5-25 % faster than
-                // one launch per pass from 180 tiles up).  On smaller levels every pass is one tile per CTA and the
-                // chain completion -> counter -> poll -> load is longer than a kernel boundary, and a waiting CTA keeps
-                // its SM: those keep one launch per pass.
-                static const int multi_min_tiles = getenv("PF_SOR_MULTI_MIN_TILES") ? atoi(getenv("PF_SOR_MULTI_MIN_TILES")) : 148;
-                if (npasses > 1 && ntiles >= multi_min_tiles && tx.ntiles > 0 && ty.ntiles > 0 && ntiles + 1 <= kCtrlWords) {
-                    SorMultiMaps m;
-                    m.phi = make_plane_map(a.phi, w, h, a.pitch, 72, kRegionH + 1);
-                    m.dxy = make_plane_map(a.dxy, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.iu = make_plane_map(a.iu, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.iv = make_plane_map(a.iv, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.bu = make_plane_map(a.bu, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.bv = make_plane_map(a.bv, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.du[0] = make_plane_map(du, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.dv[0] = make_plane_map(dv, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.du[1] = make_plane_map(du2, w, h, a.pitch, kSorRegionW, kRegionH);
-                    m.dv[1] = make_plane_map(dv2, w, h, a.pitch, kSorRegionW, kRegionH);
-                    PF_CUDA(cudaMemsetAsync(ctrl, 0, (size_t)(ntiles + 1) * sizeof(unsigned int), st));
-                    k_sor_rb_multi<T, kR, kNW><<<std::min(ntiles, sms), kNW * 32 + 32, sor_smem_bytes(), st>>>(
-                            m, du, dv, du2, dv2, w, h, a.pitch, a.alpha, a.omega, fuse, nsor - fuse * (npasses - 1), npasses,
-                            tx.ntiles, ty.ntiles, tx.step, ty.step, ctrl);
-                    if (npasses & 1) {   // pass p writes buffer (p + 1) & 1: the result of an odd number of passes is in du2/dv2
-                        std::swap(du, du2);
-                        std::swap(dv, dv2);
-                    }
-                    return 1;
-                }
-            }
-        }
         for (const SorPass& ps : schedule(w, h, nsor)) {
             launch_pass(a, ps, du, dv, du2, dv2, 0, ps.ty.ntiles);
             launches++;
@@ -363,13 +292,21 @@ class Plan : public PlanBase {
         if (fused_tma_)
             PF_CUDA(cudaFuncSetAttribute(k_fused_tma<T, kFTY, kFSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(FusedSmem<T, kFTY>) + 128)));
-        PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
-        for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
-        allocate();
-        sor_.init(P.mode, P.device, st_, P.tune);
+        try {
+            PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+            for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
+            allocate();
+            sor_.init(P.mode, P.device, st_, P.tune);
+        } catch (...) {
+            release();       // the destructor does not run for a half-built object (PF_ENOMEM is the realistic cause)
+            throw;
+        }
     }
 
-    ~Plan() override {
+    ~Plan() override { release(); }
+
+  private:
+    void release() {
         cudaSetDevice(P.device);
         if (gexec_) cudaGraphExecDestroy(gexec_);
         for (auto& gp : gexec_seq_) for (auto& g : gp) if (g) cudaGraphExecDestroy(g);
@@ -377,7 +314,14 @@ class Plan : public PlanBase {
         for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
         for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
         if (st_) cudaStreamDestroy(st_);
+        gexec_ = nullptr; graph_ = nullptr; st_ = nullptr;
+        for (auto& gp : gexec_seq_) for (auto& g : gp) g = nullptr;
+        for (auto& ev : ev_) ev = nullptr;
+        spans_.clear();
+        arena_.release();
     }
+
+  public:
 
     int levels() const override { return nlev_; }
 
@@ -397,18 +341,27 @@ class Plan : public PlanBase {
         PF_CUDA(cudaMemcpyAsync(d_in2_, im2, n, cudaMemcpyHostToDevice, st_));
     }
 
-    // enqueue (pinned destinations) or perform (pageable destinations) the three output copies
+    // enqueue (pinned destinations) or perform (pageable destinations) the output copies; an output the caller passed
+    // as NULL is not copied at all (the reference driver never reads warpI2, Par/OpticalFlowCalculation.py:74-76,
+    // and it is 60 % of the device->host bytes)
     void download_outputs(double* vx, double* vy, double* warp) {
-        size_t n = (size_t)P.h * P.w * sizeof(double);
-        HostStager* hs = ((2 + P.c) * n >= kStageMinBytes && host_is_pageable(vx) && host_is_pageable(vy) && host_is_pageable(warp))
-                                 ? HostStager::for_device(P.device) : nullptr;
+        const size_t n = (size_t)P.h * P.w * sizeof(double);
+        std::vector<CopyJob> jobs;
+        if (vx) jobs.push_back({d_vx_, vx, n});
+        if (vy) jobs.push_back({d_vy_, vy, n});
+        if (warp) jobs.push_back({d_warp_, warp, n * P.c});
+        size_t total = 0;
+        bool pageable = !jobs.empty();
+        for (const CopyJob& j : jobs) {
+            total += j.bytes;
+            pageable = pageable && host_is_pageable(j.host);
+        }
+        HostStager* hs = (pageable && total >= kStageMinBytes) ? HostStager::for_device(P.device) : nullptr;
         if (hs) {
-            hs->to_host({{d_vx_, vx, n}, {d_vy_, vy, n}, {d_warp_, warp, n * P.c}}, st_);
+            hs->to_host(jobs, st_);
             return;
         }
-        PF_CUDA(cudaMemcpyAsync(vx, d_vx_, n, cudaMemcpyDeviceToHost, st_));
-        PF_CUDA(cudaMemcpyAsync(vy, d_vy_, n, cudaMemcpyDeviceToHost, st_));
-        PF_CUDA(cudaMemcpyAsync(warp, d_warp_, n * P.c, cudaMemcpyDeviceToHost, st_));
+        for (const CopyJob& j : jobs) PF_CUDA(cudaMemcpyAsync(j.host, j.dev, j.bytes, cudaMemcpyDeviceToHost, st_));
     }
 
     void download(double* vx, double* vy, double* warp) override {

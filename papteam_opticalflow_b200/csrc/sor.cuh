@@ -313,6 +313,7 @@ struct SorPeer {
     unsigned int* wait_flag[2] = {nullptr, nullptr};     // counters in THIS device's memory
     unsigned int wait_count[2] = {0, 0};                 // CTAs of the neighbour's previous pass
     unsigned int* signal_flag[2] = {nullptr, nullptr};   // counters in the neighbours' memory (peer mapped)
+    unsigned int* error_word = nullptr;                  // set (this device's memory) when a wait ran out of time
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -392,17 +393,30 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         mbar_fence_init();
     }
     // row-band split: the neighbours' previous pass must be complete (its halo rows are in our input planes, and
-    // it no longer reads the planes this pass pushes into) before anything of this pass touches memory
+    // it no longer reads the planes this pass pushes into) before anything of this pass touches memory.  A neighbour
+    // that is merely busy (another process on its GPU, time slicing, a debugger) is an ordinary scheduling delay:
+    // the wait is bounded by wall-clock time (20 s), not by a spin count, and running out of it is reported through
+    // an error word the host checks after the solve (PF_ECUDA) -- never by a trap, which would poison the context
+    // and with it every pooled plan of the process.
+    __shared__ int peer_lost;
+    if (tid == 0) peer_lost = 0;
     if (peer.wait_flag[0] || peer.wait_flag[1]) {
         if (tid == 0) {
+            unsigned long long t_start = 0;
             for (int side = 0; side < 2; side++) {
                 if (!peer.wait_flag[side]) continue;
                 unsigned int spins = 0;
                 while (ld_acquire_sys(peer.wait_flag[side]) < peer.wait_count[side]) {
                     __nanosleep(64);
-                    if (++spins > (1u << 22)) {   // a lost neighbour must not hang the GPU (a few seconds)
-                        printf("pyflow_b200: row-band neighbour timeout (block %d side %d)\n", blockIdx.x, side);
-                        __trap();
+                    if ((++spins & 0xfffu) == 0) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (!t_start) t_start = now;
+                        if (now - t_start > 20000000000ull) {
+                            peer_lost = 1;
+                            if (peer.error_word) atomicExch(peer.error_word, 1u + (unsigned)side);
+                            break;
+                        }
                     }
                 }
             }
@@ -410,7 +424,7 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         }
     }
     __syncthreads();
-    int tile = blockIdx.x;
+    int tile = peer_lost ? ntiles : blockIdx.x;      // a lost neighbour: do nothing, still signal below
     if (tid == 0 && tile < ntiles) issue(tile);
     uint32_t parity = 0;
 
@@ -593,308 +607,6 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
             if (peer.signal_flag[0]) red_release_sys_add(peer.signal_flag[0], 1u);
             if (peer.signal_flag[1]) red_release_sys_add(peer.signal_flag[1], 1u);
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fast mode, ALL passes of one solve in one launch (single GPU): k_sor_rb_multi.
-//
-// Same tile visit as k_sor_rb_tma (TMA-staged region, register-resident red-black sweeps, exact window
-// written back to the other ping-pong buffer), but the kernel boundary between the fused-sweep passes is
-// replaced by TILE-LEVEL dependencies: tile t of pass p+1 reads rows that only the 3x3 neighbourhood of t
-// wrote in pass p (and overwrites rows that only that neighbourhood still had to read), so it may start as
-// soon as those nine tiles have finished pass p.  Every tile has a counter of completed passes in global
-// memory; a producer warp per CTA draws the next (pass, tile) ticket from a global atomic counter, spins on the
-// nine counters, and then issues the TMA loads, while the eight consumer warps are still sweeping the
-// previous tile.  Tickets are handed out in (pass, tile) order and only to CTAs that are running, so a
-// waiting producer only ever waits for tiles that resident CTAs are working on: no co-residency requirement,
-// no deadlock with other kernels sharing the GPU.  Gone are, per pass: the launch gap, the exposed load of
-// every CTA's first tile, and the idle tail of the last wave -- most of the cost of a pass on the levels
-// where a CTA sees only one or two tiles per pass.
-// All passes use the tiling of `nsw` fused sweeps; the last pass may run fewer sweeps (its window is then
-// smaller than it could be, which is harmless).  ctrl[0] is the ticket counter, ctrl[1 + t] the passes tile t
-// has completed; the host zeroes ctrl before the launch.
-// ------------------------------------------------------------------------------------------------
-struct SorMultiMaps {
-    CUtensorMap phi, dxy, iu, iv, bu, bv;
-    CUtensorMap du[2], dv[2];   // the two ping-pong buffers: pass p reads [p & 1] and writes [(p + 1) & 1]
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-template <int NTHREADS>
-__device__ __forceinline__ void consumer_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-}
-
-template <typename T, int R, int NW>
-__global__ void __launch_bounds__(NW * 32 + 32, 1)
-k_sor_rb_multi(const __grid_constant__ SorMultiMaps maps, T* __restrict__ du0, T* __restrict__ dv0, T* __restrict__ du1,
-               T* __restrict__ dv1, int W, int H, int P, T alpha, T omega, int nsw, int nsw_last, int npasses, int ntx,
-               int nty, int step_x, int step_y, unsigned int* __restrict__ ctrl) {
-    static_assert(R % 2 == 0, "R must be even so that pixel colour is a compile-time function of (r,p)");
-    typedef typename Vec2<T>::type V2;
-    typedef SorStage<T, R, NW> Stage;
-    constexpr int RH = NW * R, NC = NW * 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
-    typedef T ExBuf[2][NW][2][kSorRegionW];
-    ExBuf* ex = reinterpret_cast<ExBuf*>(smem_raw + sizeof(Stage));
-    __shared__ __align__(8) uint64_t full_bar, empty_bar, done_bar;
-    __shared__ int sm_ticket, sm_done_tile, sm_pub_count;
-
-    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int HL = 2 * nsw;
-    const int ntiles = ntx * nty;
-    const unsigned int total = (unsigned int)(ntiles * npasses);
-    const T one_m = (T)1 - omega;
-
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        mbar_init(&empty_bar, 1);
-        mbar_init(&done_bar, NW);   // one arrival per consumer warp when its part of the window is stored
-        sm_pub_count = 0;
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (wp == NW) {
-        // ---------------- helper warp: lane 16 publishes completions, lanes 0-8 are the producer ----------------
-        // (one warp, not two: every warp of the CTA gets the consumers' register allocation, and a tenth warp would
-        // push that below what the sweep loop needs)
-        if (lane == 16) {
-            // When every consumer warp has stored its part of a tile's window (done_bar), make the stores visible
-            // device-wide and bump the tile's pass counter.  Not done by a consumer thread: the fence would hold its
-            // warp -- and with it the whole CTA at the next barrier -- for a memory round trip per tile.
-            for (uint32_t dph = 0;; dph ^= 1) {
-                mbar_wait(&done_bar, dph);
-                const int t = sm_done_tile;
-                if (t < 0) return;
-                __threadfence();
-                red_release_gpu_add(ctrl + 1 + t, 1u);
-                // the slot may be reused: consumers never overwrite sm_done_tile (also not with the exit mark, which
-                // can follow the last tile immediately) before this count has caught up
-                *reinterpret_cast<volatile int*>(&sm_pub_count) = *reinterpret_cast<volatile int*>(&sm_pub_count) + 1;
-            }
-        }
-        if (lane > 8) return;
-        // Producer.  The ticket of the NEXT tile is drawn and its nine dependencies are polled (one lane each, so the
-        // polls are one memory round trip, not nine) while the consumers still work on the current tile; when they
-        // release the stage the loads go out at once.
-        constexpr unsigned PM = 0x1ffu;
-        unsigned int ticket = 0;
-        if (lane == 0) ticket = atomicAdd(ctrl, 1u);
-        ticket = __shfl_sync(PM, ticket, 0);
-        uint32_t eph = 0;
-        for (bool first = true;; first = false) {
-            const bool live = ticket < total;
-            const int pass = live ? (int)(ticket / (unsigned)ntiles) : 0, tile = live ? (int)(ticket % (unsigned)ntiles) : 0;
-            const int tx = tile % ntx, ty = tile / ntx;
-            if (live && pass > 0) {
-                const int nx = tx + lane % 3 - 1, ny = ty + lane / 3 - 1;
-                if (nx >= 0 && nx < ntx && ny >= 0 && ny < nty) {
-                    const unsigned int* c = ctrl + 1 + ny * ntx + nx;
-                    unsigned int spins = 0;
-                    while (ld_acquire_gpu(c) < (unsigned)pass) {
-                        __nanosleep(32);
-                        if (++spins > (1u << 24)) {   // must not hang the GPU
-                            printf("pyflow_b200: SOR tile dependency timeout (block %d ticket %u = pass %d tile %d waits for tile %d at %u; tickets drawn %u)\n",
-                                   blockIdx.x, ticket, pass, tile, ny * ntx + nx, ld_acquire_gpu(c), ld_acquire_gpu(ctrl));
-                            __trap();
-                        }
-                    }
-                }
-            }
-            __syncwarp(PM);
-            if (lane == 0) {
-                // the loads go through the async proxy: fence here, off the critical path (the stage is usually still busy)
-                if (live && pass > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
-                if (!first) mbar_wait(&empty_bar, eph);   // the consumers have pulled the previous tile out of the stage
-                if (!live) {
-                    sm_ticket = -1;
-                    mbar_expect_tx(&full_bar, 0);   // plain arrival: releases the consumers, who then leave
-                } else {
-                    sm_ticket = (int)ticket;
-                    const int rx0 = tx * step_x, ry0 = ty * step_y;
-                    const uint32_t bytes = (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW + (pass > 0 ? 7 : 5) * RH * kSorRegionW));
-                    mbar_expect_tx(&full_bar, bytes);
-                    tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
-                    tma_load_2d(&st.pl[0][0][0], &maps.dxy, rx0, ry0, &full_bar);
-                    tma_load_2d(&st.pl[1][0][0], &maps.iu, rx0, ry0, &full_bar);
-                    tma_load_2d(&st.pl[2][0][0], &maps.iv, rx0, ry0, &full_bar);
-                    tma_load_2d(&st.pl[3][0][0], &maps.bu, rx0, ry0, &full_bar);
-                    tma_load_2d(&st.pl[4][0][0], &maps.bv, rx0, ry0, &full_bar);
-                    if (pass > 0) {   // pass 0 starts from du = dv = 0
-                        tma_load_2d(&st.pl[5][0][0], &maps.du[pass & 1], rx0, ry0, &full_bar);
-                        tma_load_2d(&st.pl[6][0][0], &maps.dv[pass & 1], rx0, ry0, &full_bar);
-                    }
-                }
-            }
-            if (!first) eph ^= 1;
-            if (!live) return;
-            if (lane == 0) ticket = atomicAdd(ctrl, 1u);
-            ticket = __shfl_sync(PM, ticket, 0);
-        }
-    }
-
-    // ---------------- consumer warps ----------------
-    uint32_t parity = 0;
-    int my_tiles = 0;   // tiles this CTA has finished
-    auto hand_to_publisher = [&](int value) {
-        if (tid == 0) {
-            while (*reinterpret_cast<volatile int*>(&sm_pub_count) < my_tiles) {}   // previous hand-over consumed
-            sm_done_tile = value;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&done_bar);
-    };
-    for (;;) {
-        mbar_wait(&full_bar, parity);
-        parity ^= 1;
-        const int ticket = sm_ticket;
-        if (ticket < 0) {
-            hand_to_publisher(-1);   // releases the publisher warp
-            break;
-        }
-        const int pass = ticket / ntiles, tile = ticket - pass * ntiles;
-        const int tx = tile % ntx, ty = tile / ntx;
-        const int rx0 = tx * step_x, ry0 = ty * step_y;   // even by construction
-        const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
-        const bool has_input = pass > 0;
-        const int sweeps = pass == npasses - 1 ? nsw_last : nsw;
-
-        T w[R][2], dxy[R][2], iu[R][2], iv[R][2], bu[R][2], bv[R][2], du[R][2], dv[R][2];
-        T wl[R], wr[R], wu[2];   // wl / wr: weights towards the neighbouring lanes' columns, zero at the region edge
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = wp * R + r;
-            V2 t = *reinterpret_cast<const V2*>(&st.phi[row + 1][2 * lane + 4]);
-            w[r][0] = t.x * alpha; w[r][1] = t.y * alpha;
-            wl[r] = lane == 0 ? (T)0 : st.phi[row + 1][2 * lane + 3] * alpha;
-            wr[r] = lane == 31 ? (T)0 : w[r][1];
-            t = *reinterpret_cast<const V2*>(&st.pl[0][row][2 * lane]); dxy[r][0] = t.x; dxy[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[1][row][2 * lane]); iu[r][0] = t.x; iu[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[2][row][2 * lane]); iv[r][0] = t.x; iv[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[3][row][2 * lane]); bu[r][0] = t.x; bu[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[4][row][2 * lane]); bv[r][0] = t.x; bv[r][1] = t.y;
-            if (has_input) {
-                t = *reinterpret_cast<const V2*>(&st.pl[5][row][2 * lane]); du[r][0] = t.x; du[r][1] = t.y;
-                t = *reinterpret_cast<const V2*>(&st.pl[6][row][2 * lane]); dv[r][0] = t.x; dv[r][1] = t.y;
-            } else {
-                du[r][0] = du[r][1] = dv[r][0] = dv[r][1] = 0;
-            }
-        }
-        {
-            V2 t = *reinterpret_cast<const V2*>(&st.phi[wp * R][2 * lane + 4]);
-            wu[0] = t.x * alpha; wu[1] = t.y * alpha;
-        }
-        auto publish = [&](int b) {
-            *reinterpret_cast<V2*>(&ex[b][0][wp][0][2 * lane]) = V2{du[0][0], du[0][1]};
-            *reinterpret_cast<V2*>(&ex[b][1][wp][0][2 * lane]) = V2{dv[0][0], dv[0][1]};
-            *reinterpret_cast<V2*>(&ex[b][0][wp][1][2 * lane]) = V2{du[R - 1][0], du[R - 1][1]};
-            *reinterpret_cast<V2*>(&ex[b][1][wp][1][2 * lane]) = V2{dv[R - 1][0], dv[R - 1][1]};
-        };
-        int buf = 0;
-        publish(0);
-        consumer_barrier<NC>();          // stage consumed by every consumer, exchange rows published
-        if (tid == 0) mbar_arrive(&empty_bar);   // the producer may refill the stage: overlaps the sweeps below
-
-        auto update = [&](const int r, const int c, T up_du, T up_dv, T dn_du, T dn_dv) {
-            const int p = (r + c) & 1;
-            T lw, rw, ldu, ldv, rdu, rdv;
-            if (p == 1) {
-                lw = w[r][0]; ldu = du[r][0]; ldv = dv[r][0];
-                rw = wr[r];
-                rdu = __shfl_down_sync(0xffffffffu, du[r][0], 1);
-                rdv = __shfl_down_sync(0xffffffffu, dv[r][0], 1);
-            } else {
-                lw = wl[r];
-                ldu = __shfl_up_sync(0xffffffffu, du[r][1], 1);
-                ldv = __shfl_up_sync(0xffffffffu, dv[r][1], 1);
-                rw = w[r][0];
-                rdu = du[r][1]; rdv = dv[r][1];
-            }
-            T uw, udu, udv, ddu, ddv;
-            if (r > 0) { uw = w[r - 1][p]; udu = du[r - 1][p]; udv = dv[r - 1][p]; }
-            else       { uw = wu[p];       udu = up_du;        udv = up_dv; }
-            if (r < R - 1) { ddu = du[r + 1][p]; ddv = dv[r + 1][p]; }
-            else           { ddu = dn_du;        ddv = dn_dv; }
-            const T cw = w[r][p];
-            T s1 = bu[r][p] + lw * ldu + rw * rdu + uw * udu + cw * ddu;
-            T s2 = bv[r][p] + lw * ldv + rw * rdv + uw * udv + cw * ddv;
-            s1 -= dxy[r][p] * dv[r][p];
-            T nu = one_m * du[r][p] + iu[r][p] * s1;
-            s2 -= dxy[r][p] * nu;
-            T nv = one_m * dv[r][p] + iv[r][p] * s2;
-            du[r][p] = nu;
-            dv[r][p] = nv;
-        };
-        for (int s = 0; s < sweeps; s++) {
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int p_top = c & 1, p_bot = (R - 1 + c) & 1;
-                T up_du = 0, up_dv = 0, dn_du = 0, dn_dv = 0;
-                if (wp > 0) {
-                    up_du = ex[buf][0][wp - 1][1][2 * lane + p_top];
-                    up_dv = ex[buf][1][wp - 1][1][2 * lane + p_top];
-                }
-                if (wp < NW - 1) {
-                    dn_du = ex[buf][0][wp + 1][0][2 * lane + p_bot];
-                    dn_dv = ex[buf][1][wp + 1][0][2 * lane + p_bot];
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) update(r, c, up_du, up_dv, dn_du, dn_dv);
-                buf ^= 1;
-                publish(buf);
-                consumer_barrier<NC>();
-            }
-        }
-
-        // write back the window that is still exact, to the buffer the next pass reads
-        T* const du_out = (pass & 1) ? du0 : du1;
-        T* const dv_out = (pass & 1) ? dv0 : dv1;
-        const int ox_lo = tx > 0 ? rx0 + HL : 0;
-        const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
-        const int oy_lo = ty > 0 ? ry0 + HL : 0;
-        const int oy_hi = (ry0 + RH >= H) ? H : ry0 + RH - HL;
-        {
-            const bool v0 = xa >= ox_lo && xa < ox_hi, v1 = xa + 1 >= ox_lo && xa + 1 < ox_hi;
-            const int r_lo = oy_lo - ya;
-            const unsigned r_n = (unsigned)max(oy_hi - oy_lo, 0);
-            char* const pu = reinterpret_cast<char*>(du_out) + ((size_t)ya * P + xa) * sizeof(T);
-            const ptrdiff_t to_dv = reinterpret_cast<char*>(dv_out) - reinterpret_cast<char*>(du_out);
-            const unsigned pitch_b = (unsigned)P * (unsigned)sizeof(T);
-            if (v0 && v1) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    char* q = pu + (size_t)((unsigned)r * pitch_b);
-                    if ((unsigned)(r - r_lo) < r_n) {
-                        *reinterpret_cast<V2*>(q) = V2{du[r][0], du[r][1]};
-                        *reinterpret_cast<V2*>(q + to_dv) = V2{dv[r][0], dv[r][1]};
-                    }
-                }
-            } else if (v0 || v1) {
-                const int k = v1 ? 1 : 0;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    T* q = reinterpret_cast<T*>(pu + (size_t)((unsigned)r * pitch_b)) + k;
-                    if ((unsigned)(r - r_lo) < r_n) {
-                        *q = v1 ? du[r][1] : du[r][0];
-                        *reinterpret_cast<T*>(reinterpret_cast<char*>(q) + to_dv) = v1 ? dv[r][1] : dv[r][0];
-                    }
-                }
-            }
-        }
-        // this warp's part of the window is stored (and the tile's region was read long ago): the publisher warp
-        // announces the tile's completion once all consumer warps have arrived
-        hand_to_publisher(tile);
-        my_tiles++;
     }
 }
 

@@ -8,6 +8,7 @@
 // used.  Buffers that are already pinned (pf_host_alloc, cudaHostRegister) bypass this and are copied directly.
 // One stager per device, created on first use; a mutex serialises staged transfers on a device.
 #pragma once
+#include <sched.h>
 #include <atomic>
 #include <cstring>
 #include <memory>
@@ -40,7 +41,8 @@ class HostStager {
 
     static HostStager* for_device(int dev) {
         static std::mutex mu;
-        static std::vector<std::unique_ptr<HostStager>> all;
+        // leaked on purpose: a static destructor would make CUDA calls while the runtime is being torn down at exit
+        static std::vector<std::unique_ptr<HostStager>>& all = *new std::vector<std::unique_ptr<HostStager>>();
         std::lock_guard<std::mutex> g(mu);
         if (disabled()) return nullptr;
         if ((int)all.size() <= dev) all.resize((size_t)dev + 1);
@@ -90,7 +92,17 @@ class HostStager {
     explicit HostStager(int dev) : dev_(dev) {
         int n = 0;
         if (const char* e = getenv("PF_STAGER_THREADS")) n = atoi(e);
-        if (n < 1) n = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+        if (n < 1) {
+            // the cores this process may run on, shared between the processes of the node (one per GPU under
+            // torchrun: LOCAL_WORLD_SIZE) -- 8 ranks x 8 stager threads on 32 cores was the round-1 default and
+            // lost more to oversubscription than it gained
+            unsigned cores = std::thread::hardware_concurrency();
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = (unsigned)CPU_COUNT(&set);
+            unsigned procs = 1;
+            if (const char* e = getenv("LOCAL_WORLD_SIZE")) procs = (unsigned)std::max(1, atoi(e));
+            n = (int)std::min(8u, std::max(2u, cores / (2 * procs)));
+        }
         workers_.resize((size_t)n);
         if (cudaSetDevice(dev_) != cudaSuccess) return;
         for (auto& w : workers_) {

@@ -15,7 +15,6 @@ freshly allocated float64 arrays -- exactly the reference's contract.  Keyword-o
     device  CUDA device index (default 0)
     profile True: run eagerly with CUDA events per phase and fill every timing key
 """
-import collections
 import ctypes as C
 import os
 import threading
@@ -85,7 +84,24 @@ def _check_image(name, a):
 
 
 def _ptr(a):
-    return a.ctypes.data_as(dp)
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def _check_outputs(out, h, w, c):
+    """Caller-supplied outputs are written by native code as raw double*: require exactly what the module itself would
+    allocate (Par/pyflow.pyx:47-52: float64, C-contiguous, (h, w), (h, w), (h, w, c)).  Any of the three may be None:
+    that output is then not copied back from the device."""
+    try:
+        vx, vy, wi = out
+    except (TypeError, ValueError):
+        raise ValueError("outputs must be a (vx, vy, warpI2) triple")
+    for name, a, shape in (("vx", vx, (h, w)), ("vy", vy, (h, w)), ("warpI2", wi, (h, w, c))):
+        if a is None:
+            continue
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.shape != shape or not a.flags["C_CONTIGUOUS"] \
+                or not a.flags["WRITEABLE"]:
+            raise ValueError("output %s must be a writeable C-contiguous float64 array of shape %s" % (name, shape))
+    return vx, vy, wi
 
 
 class FlowPlan(object):
@@ -108,9 +124,18 @@ class FlowPlan(object):
         self.levels = _lib.lib().pf_plan_levels(self._h)
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            _lib.lib().pf_plan_destroy(self._h)
-            self._h = C.c_void_p()
+        lock = getattr(self, "_lock", None)
+        if lock is None:
+            return
+        with lock:                           # never under a native call of another thread
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().pf_plan_destroy(self._h)
+                self._h = C.c_void_p()
+
+    def _handle(self):
+        if not self._h.value:
+            raise ValueError("plan is closed")
+        return self._h
 
     __del__ = close
 
@@ -127,28 +152,28 @@ class FlowPlan(object):
     def execute(self, im1, im2, out=None):
         """H2D + solve + D2H.  Returns (timings_ms ndarray, vx, vy, warpI2)."""
         self._check_pair(im1, im2)
-        vx, vy, wi = out if out is not None else self._outputs()
+        vx, vy, wi = _check_outputs(out, *self.shape) if out is not None else self._outputs()
         t = np.zeros(_lib.PF_NUM_TIMINGS)
         with self._lock:
-            check(_lib.lib().pf_plan_execute(self._h, _ptr(vx), _ptr(vy), _ptr(wi), _ptr(im1), _ptr(im2), _ptr(t)))
+            check(_lib.lib().pf_plan_execute(self._handle(), _ptr(vx), _ptr(vy), _ptr(wi), _ptr(im1), _ptr(im2), _ptr(t)))
         return t, vx, vy, wi
 
     def upload(self, im1, im2):
         self._check_pair(im1, im2)
         with self._lock:
-            check(_lib.lib().pf_plan_upload(self._h, _ptr(im1), _ptr(im2)))
+            check(_lib.lib().pf_plan_upload(self._handle(), _ptr(im1), _ptr(im2)))
 
     def solve(self, repeats=1):
         """Device-only solve on the resident inputs; returns total milliseconds (CUDA events)."""
         ms = C.c_double()
         with self._lock:
-            check(_lib.lib().pf_plan_solve(self._h, int(repeats), C.byref(ms)))
+            check(_lib.lib().pf_plan_solve(self._handle(), int(repeats), C.byref(ms)))
         return ms.value
 
     def download(self, out=None):
-        vx, vy, wi = out if out is not None else self._outputs()
+        vx, vy, wi = _check_outputs(out, *self.shape) if out is not None else self._outputs()
         with self._lock:
-            check(_lib.lib().pf_plan_download(self._h, _ptr(vx), _ptr(vy), _ptr(wi)))
+            check(_lib.lib().pf_plan_download(self._handle(), _ptr(vx), _ptr(vy), _ptr(wi)))
         return vx, vy, wi
 
     def profile(self):
@@ -156,13 +181,13 @@ class FlowPlan(object):
         t = np.zeros(_lib.PF_NUM_TIMINGS)
         cnt = np.zeros(8)
         with self._lock:
-            check(_lib.lib().pf_plan_profile(self._h, _ptr(t), _ptr(cnt)))
+            check(_lib.lib().pf_plan_profile(self._handle(), _ptr(t), _ptr(cnt)))
         return t, cnt
 
     def mixture_params(self):
         """(alpha, sigma, beta) per feature channel after the last solve (Gaussian-mixture noise model only)."""
         a, s, b = np.zeros(16), np.zeros(16), np.zeros(16)
-        n = _lib.lib().pf_plan_mixture_params(self._h, _ptr(a), _ptr(s), _ptr(b), 16)
+        n = _lib.lib().pf_plan_mixture_params(self._handle(), _ptr(a), _ptr(s), _ptr(b), 16)
         if n < 0:
             check(n)
         return a[:n].copy(), s[:n].copy(), b[:n].copy()
@@ -171,7 +196,7 @@ class FlowPlan(object):
         """(levels, PF_NUM_TIMINGS) array of per-level phase milliseconds from the last profile()."""
         out = np.zeros((self.levels, _lib.PF_NUM_TIMINGS))
         with self._lock:
-            check(_lib.lib().pf_plan_level_timings(self._h, _ptr(out), self.levels))
+            check(_lib.lib().pf_plan_level_timings(self._handle(), _ptr(out), self.levels))
         return out
 
 
@@ -182,23 +207,6 @@ def multi_solve(plans, repeats=1):
     ms = C.c_double()
     check(_lib.lib().pf_multi_solve(arr, len(plans), int(repeats), C.byref(ms)))
     return ms.value
-
-
-_plans = collections.OrderedDict()
-_plans_lock = threading.Lock()
-_MAX_PLANS = 4
-
-
-def _get_plan(key, **kw):
-    with _plans_lock:
-        p = _plans.pop(key, None)
-        if p is None:
-            p = FlowPlan(**kw)
-            while len(_plans) >= _MAX_PLANS:
-                _, old = _plans.popitem(last=False)
-                old.close()
-        _plans[key] = p
-        return p
 
 
 def _timing_dict(t_ms):
@@ -236,15 +244,26 @@ def coarse2fine_flow(Im1, Im2, *args, **kwargs):
         raise ValueError("Im1 and Im2 must have the same shape, got %s and %s" % (Im1.shape, Im2.shape))
     h, w, c = Im1.shape
     mid = _mode_id(mode)
-    key = (h, w, c, tuple(sorted(p.items())), levels, mid, int(device), get_solver_variant())
-    plan = _get_plan(key, h=h, w=w, c=c, levels=levels, mode=mid, device=device, tuning="latency", **p)   # one pair at a time
-    t, vx, vy, wi = plan.execute(Im1, Im2)
+    # One pair at a time goes through the library's own one-shot entry points: they draw an idle plan (arena + captured
+    # graph, latency-tuned) from the native pool, which never hands a plan to two callers and never destroys one in use.
+    L = _lib.lib()
+    vx, vy, wi = np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))
+    t = np.zeros(_lib.PF_NUM_TIMINGS)
     if fork:
+        check(L.pf_coarse2fine_flow_levels(_ptr(vx), _ptr(vy), _ptr(wi), _ptr(Im1), _ptr(Im2), levels, 1, h, w, c, mid,
+                                           int(device), _ptr(t)))
         if profile:
-            tp, _ = plan.profile()
+            plan = FlowPlan(h, w, c, levels=levels, mode=mid, device=device, tuning="latency", **p)   # private to this call
+            try:
+                plan.upload(Im1, Im2)
+                tp, _ = plan.profile()
+            finally:
+                plan.close()
             for i in range(1, 10):
                 t[i] = tp[i]
         return _timing_dict(t), vx, vy, wi
+    check(L.pf_coarse2fine_flow(_ptr(vx), _ptr(vy), _ptr(wi), _ptr(Im1), _ptr(Im2), p["alpha"], p["ratio"], p["minWidth"],
+                                p["nOuter"], p["nInner"], p["nSOR"], p["colType"], h, w, c, mid, int(device), _ptr(t)))
     return vx, vy, wi
 
 
@@ -392,6 +411,10 @@ def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFP
     h, w, c = pairs[0][0].shape
     if outs is None:
         outs = [(np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, c))) for _ in range(n)]
+    else:
+        if len(outs) != n:
+            raise ValueError("outs must hold one (vx, vy, warpI2) triple per pair")
+        outs = [_check_outputs(o, h, w, c) for o in outs]     # entries may be None: that output is not copied back
     arr = lambda xs: (dp * n)(*[_ptr(x) for x in xs])  # noqa: E731
     dev = (C.c_int * len(devices))(*devices)
     secs = C.c_double()
@@ -401,3 +424,11 @@ def coarse2fine_flow_batch(pairs, alpha=0.012, ratio=0.75, minWidth=20, nOuterFP
                           int(nSORIterations), int(colType), h, w, c, _mode_id(mode), dev, len(devices),
                           C.byref(secs)))
     return outs, secs.value
+
+
+def batch_last_stats():
+    """Event-timed legs of the last coarse2fine_flow_batch call (pf_batch_last_stats): dict(pairs, workers, seconds,
+    h2d_ms, solve_ms, d2h_ms, call_ms) -- means per pair."""
+    st = np.zeros(8)
+    check(_lib.lib().pf_batch_last_stats(_ptr(st)))
+    return dict(pairs=int(st[0]), workers=int(st[1]), seconds=st[2], h2d_ms=st[3], solve_ms=st[4], d2h_ms=st[5], call_ms=st[6])
