@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 H, W, CH = 1080, 1920, 3
 PARAMS = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30, colType=0)
 WORKLOAD = "HoChiMinhTraffic_10FPS_1920 pair, 1920x1080 RGB, defaults alpha=0.012 ratio=0.75 minWidth=20 (15 levels) 7/1/30"
+L2_NOTE = "no explicit flush: per-solve working set ~0.5 GB of planes per pair x 24 pairs in flight >> 126 MB L2"
 REF_COLLECTION = "/root/reference/images_New/HoChiMinhTraffic_10FPS_1920"
 
 
@@ -226,7 +227,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "frame_pairs_per_sec_1920w", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": frames.data,
-            "config": {"workload": WORKLOAD},
+            "config": {"workload": WORKLOAD, "l2": L2_NOTE},
             "setup": {"implementation": "reference OpenMP build (Code/Parallel, unmodified, racy for nCores > 1), nCores=%d" % cores,
                       "pairs_per_step": 1},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
@@ -473,11 +474,10 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_pair": ms / args.steps / B,
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode.startswith("fp32") else "f64", "data": frames.data,
-            "config": {"workload": WORKLOAD},          # the same dict in the reference arm's line
+            "config": {"workload": WORKLOAD, "l2": L2_NOTE},          # the same dict in the reference arm's line
             "setup": {"mode": args.mode, "pairs_per_gpu_per_step": B,
                       "pairs": "sequence pairs %s on rank 0 (pair p -> GPU p mod N)" % ",".join("%d-%d" % q for q in mine[:8]),
                       "concurrency": "%d pairs in flight per GPU, one CUDA stream + graph each" % B,
-                      "l2": "per-solve working set ~0.5 GB of planes > 126 MB L2 (no explicit flush)",
                       "host_buffers": "pinned" if pinned else "pageable"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * h2d_pair),

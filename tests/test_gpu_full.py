@@ -472,26 +472,57 @@ def test_pageable_buffers_through_the_stager_equal_the_direct_copy_path(monkeypa
     assert np.abs(want_ba[0] - want[0]).max() > 1e-3
 
 
-def test_multi_pass_sor_kernel_is_bit_identical(monkeypatch):
-    """PF_SOR_MULTI=1 runs all fused-sweep passes of a solve in ONE launch of k_sor_rb_multi (tile-level dependencies
-    through per-tile pass counters instead of kernel boundaries; opt-in).  The red-black update does
-    not depend on tiling or pass structure: same bits as the default path, also with a sweep count that leaves a short
-    last pass."""
-    import subprocess, sys, os
-    code = (
-        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "import pyflow; from conftest import load_frame\n"
-        "a, b = load_frame(960, 1), load_frame(960, 2)\n"
-        "out = []\n"
-        "for nsor in (30, 17):\n"
-        "    u, v, w = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 3, 1, nsor, 0, mode='fp32_redblack')\n"
-        "    out += [u, v]\n"
-        "np.save(sys.argv[1], np.stack(out))\n"
-    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    res = {}
-    for flag in ("0", "1"):   # the switch is read when the library initialises a solver: one process per setting
-        path = "/tmp/pf_multi_%s.npy" % flag
-        env = dict(os.environ, PF_SOR_MULTI=flag)
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
-        res[flag] = np.load(path)
-    assert np.array_equal(res["0"], res["1"])
+def test_null_outputs_are_skipped_and_bad_outputs_rejected():
+    """pf_plan_execute / pf_batch_flow copy back only the outputs the caller asks for (NULL = skip; the reference
+    driver never reads warpI2), and caller-supplied output arrays are validated before native code writes them."""
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    plan = pyflow.FlowPlan(135, 240, 3, mode="fp32_redblack")
+    _, vx, vy, wi = plan.execute(a, b)
+    ox, oy = np.full((135, 240), 7.0), np.full((135, 240), 7.0)
+    plan.execute(a, b, out=(ox, oy, None))
+    assert np.array_equal(ox, vx) and np.array_equal(oy, vy)
+    ow = np.full((135, 240, 3), 7.0)
+    plan.download(out=(None, None, ow))
+    assert np.array_equal(ow, wi)
+    outs = [(np.zeros((135, 240)), np.zeros((135, 240)), None), (np.zeros((135, 240)), None, np.zeros((135, 240, 3)))]
+    got, _ = pyflow.coarse2fine_flow_batch([(a, b), (a, b)], mode="fp32_redblack", outs=outs)
+    assert np.array_equal(got[0][0], vx) and np.array_equal(got[0][1], vy) and got[0][2] is None
+    assert np.array_equal(got[1][0], vx) and np.array_equal(got[1][2], wi)
+    st = pyflow.batch_last_stats()
+    assert st["pairs"] == 2 and st["solve_ms"] > 0 and st["h2d_ms"] >= 0 and st["workers"] >= 1
+    for bad in ((ox.astype(np.float32), oy, ow), (ox[:, :100], oy, ow), (ox, oy, ow[..., :2]), (ox.T.copy().T, oy, ow), (ox, oy)):
+        with pytest.raises(ValueError):
+            plan.execute(a, b, out=bad)
+        with pytest.raises(ValueError):
+            pyflow.coarse2fine_flow_batch([(a, b)], mode="fp32_redblack", outs=[bad])
+    with pytest.raises(ValueError):
+        plan.download(out=(ox, oy, ow.astype(np.float32)))
+    plan.close()
+    with pytest.raises(ValueError):
+        plan.solve(1)                       # closed plans fail in Python, not in native code
+
+
+def test_one_shot_calls_from_many_threads_share_the_native_pool():
+    """The drop-in entry point draws plans from the library's pool (never shared between callers, never destroyed
+    while in use): concurrent callers with more distinct shapes than the old 4-entry Python cache held."""
+    import threading
+    a, b = load_frame(240, 1), load_frame(240, 2)
+    shapes = [(135 - 4 * k, 240 - 8 * k) for k in range(6)]
+    want = {}
+    for h, w in shapes:
+        want[(h, w)] = pyflow.coarse2fine_flow(np.ascontiguousarray(a[:h, :w]), np.ascontiguousarray(b[:h, :w]), 6, mode="fp32_redblack")[1]
+    errs = []
+    def work(seed):
+        try:
+            for k in range(6):
+                h, w = shapes[(seed + k) % len(shapes)]
+                got = pyflow.coarse2fine_flow(np.ascontiguousarray(a[:h, :w]), np.ascontiguousarray(b[:h, :w]), 6, mode="fp32_redblack")[1]
+                assert np.array_equal(got, want[(h, w)])
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
