@@ -35,6 +35,12 @@ extern "C" {
 #define PF_MODE_FP32_REDBLACK  1 /* FP32, red-black SOR with fused sweeps: the fast mode */
 #define PF_MODE_FP64_REDBLACK  2 /* FP64 arithmetic, red-black ordering */
 #define PF_MODE_FP32_WAVEFRONT 3 /* FP32 arithmetic, lexicographic ordering */
+#define PF_MODE_FP32_HYBRID    4 /* the fast mode with the reference's lexicographic order on the coarse pyramid levels
+                                    (width <= PF_HYBRID_MAX_WIDTH) and red-black above: an ordering difference on a coarse,
+                                    under-iterated level is multiplied by 1/ratio per level on the way up, and where the flow
+                                    leaves the frame (weak data term) that alone moves single pixels by more than 0.5 px
+                                    (BASELINE config 5); with this mode they stay within 0.2 px */
+#define PF_HYBRID_MAX_WIDTH    400
 
 /* ---- alternative solver branches ----------------------------------------
  * The reference selects them through two process-global PUBLIC STATIC members,

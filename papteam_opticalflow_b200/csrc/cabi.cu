@@ -59,7 +59,7 @@ int check_device(int device) {
 }
 
 int check_mode(int mode) {
-    if (mode < 0 || mode > 3) return fail(PF_EINVAL, "unknown mode " + std::to_string(mode));
+    if (mode < 0 || mode > 4) return fail(PF_EINVAL, "unknown mode " + std::to_string(mode));
     return PF_OK;
 }
 

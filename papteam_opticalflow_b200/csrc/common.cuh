@@ -91,5 +91,9 @@ inline bool same_solver(const Params& a, const Params& b) {
 
 inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }
 inline bool mode_is_lex(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP32_WAVEFRONT; }
+// does a pyramid level of this width run its SOR solves in the reference's lexicographic order?
+inline bool mode_lex_at(int mode, int level_width) {
+    return mode_is_lex(mode) || (mode == PF_MODE_FP32_HYBRID && level_width <= PF_HYBRID_MAX_WIDTH);
+}
 
 }  // namespace pf

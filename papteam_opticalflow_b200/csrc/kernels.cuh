@@ -94,6 +94,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+static __global__ void k_fill_f64(double* p, double v, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 static __global__ void k_minmax_init(unsigned int* mm) {
     mm[0] = 0x7f800000u;   // +inf
     mm[1] = 0u;

@@ -14,6 +14,7 @@
 #include "geometry.hpp"
 #include "kernels.cuh"
 #include "sor.cuh"
+#include "sor_lex.cuh"
 #include "fused_tma.cuh"
 #include "staging.hpp"
 
@@ -132,12 +133,21 @@ struct SorRunner {
     static constexpr int kR = kF64 ? 2 : PF_SOR_R;
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, simple_rb = false, use_tma = true;
+    bool lex = false, hybrid = false, simple_rb = false, use_tma = true;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     int tune = PF_TUNE_THROUGHPUT;
+    int lex_from = -1;   // experiment (PF_LEX_FROM=k): pyramid levels >= k use the lexicographic kernel in every mode
+    bool lex_band = true;          // k_sor_lex (band-march) instead of the grid-synchronised k_sor_wavefront (PF_LEX_IMPL=coop)
+    static constexpr int kLexNS = 8;
+    static constexpr size_t kLexFlagWords = 1u << 16;
+    int* lex_flags = nullptr;      // ticket + abort + progress words of k_sor_lex, zeroed before every launch
+    int* lex_err = nullptr;        // sticky error word
     cudaStream_t st = nullptr;
 
     SorRunner() = default;
+    ~SorRunner() {
+        if (lex_flags) cudaFree(lex_flags);
+    }
     SorRunner(const SorRunner&) = delete;
     SorRunner& operator=(const SorRunner&) = delete;
 
@@ -146,6 +156,7 @@ struct SorRunner {
 
     void init(int mode, int device, cudaStream_t stream, int tuning = PF_TUNE_THROUGHPUT) {
         lex = mode_is_lex(mode);
+        hybrid = mode == PF_MODE_FP32_HYBRID;
         st = stream;
         tune = tuning;
         const char* e = getenv("PF_SOR_FUSE");
@@ -154,15 +165,26 @@ struct SorRunner {
         simple_rb = e && atoi(e);
         e = getenv("PF_SOR_TMA");
         use_tma = !(e && !atoi(e));
+        e = getenv("PF_LEX_FROM");
+        lex_from = e ? atoi(e) : -1;
         PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        if (!lex && !simple_rb && use_tma) {
+        if (!lex && !simple_rb && use_tma) {   // (the hybrid mode needs both kernels)
             size_t bytes = sor_smem_bytes();
             PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, kR, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             int per_sm = 1;
             PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_rb_tma<T, kR, kNW>, kNW * 32, bytes));
             ctas_per_sm = std::max(1, per_sm);
         }
-        if (lex) {
+        e = getenv("PF_LEX_IMPL");
+        lex_band = !(e && !strcmp(e, "coop"));
+        if ((lex || hybrid || lex_from >= 0) && lex_band) {
+            PF_CUDA(cudaFuncSetAttribute(k_sor_lex<T, kLexNS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LexCfg<T, kLexNS>::smem_bytes()));
+            PF_CUDA(cudaMalloc(&lex_flags, (kLexFlagWords + 64) * sizeof(int)));
+            PF_CUDA(cudaMemset(lex_flags, 0, (kLexFlagWords + 64) * sizeof(int)));
+            lex_err = lex_flags + kLexFlagWords;
+        }
+        if ((lex || hybrid || lex_from >= 0) && !lex_band) {
             int coop = 0, per_sm = 0;
             PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
             if (!coop) throw Error(PF_EUNSUPPORTED, "device lacks cooperative launch");
@@ -199,6 +221,46 @@ struct SorRunner {
         return v;
     }
 
+    // developer aid (PF_LEX_STATS=1): one synchronous launch of the instrumented kernel, per-CTA clocks to stderr
+    void lex_stats(LexArgs<T> la) {
+        const int n = la.NI * la.NK;
+        long long* d = nullptr;
+        PF_CUDA(cudaMalloc(&d, (size_t)n * 16 * sizeof(long long)));
+        PF_CUDA(cudaMemset(d, 0, (size_t)n * 16 * sizeof(long long)));
+        la.stats = d;
+        PF_CUDA(cudaFuncSetAttribute(k_sor_lex<T, kLexNS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)LexCfg<T, kLexNS>::smem_bytes()));
+        k_sor_lex<T, kLexNS, true><<<n, LexCfg<T, kLexNS>::THREADS, LexCfg<T, kLexNS>::smem_bytes(), st>>>(la);
+        PF_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h((size_t)n * 16);
+        PF_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        long long t0 = 0, t1 = 0;
+        for (int i = 0; i < n; i++)
+            if (h[i * 16 + 2]) { t0 = t0 ? std::min(t0, h[i * 16 + 2]) : h[i * 16 + 2]; t1 = std::max(t1, h[i * 16 + 3]); }
+        fprintf(stderr, "k_sor_lex %dx%d nsor=%d NI=%d NK=%d: %lld ns first start to last end\n", la.w, la.h, la.nsor, la.NI, la.NK, t1 - t0);
+        for (int i = 0; i < n; i++) {
+            const long long* o = &h[i * 16];
+            if (!o[2]) continue;
+            fprintf(stderr, "  I=%lld K=%lld start %7lld ns end %7lld ns | cycles %8lld wait_plane %8lld wait_loader %8lld steps %lld -> %lld cyc/step busy\n", o[0], o[1],
+                    o[2] - t0, o[3] - t0, o[7], o[4], o[5], o[6], (o[7] - o[4] - o[5]) / std::max(1ll, o[6]));
+            fprintf(stderr, "      passes step 0/64/128/... at us:");
+            for (int q = 0; q < 8; q++) if (o[8 + q]) fprintf(stderr, " %.1f", (o[8 + q] - t0) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    }
+
+    // after the stream has been synchronised: did a hand-off of k_sor_lex time out?
+    void check_lex() {
+        if (!lex_err) return;
+        int e = 0;
+        PF_CUDA(cudaMemcpy(&e, lex_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset(lex_err, 0, sizeof(int));
+            throw Error(PF_ECUDA, "lexicographic SOR: a hand-off between bands timed out");
+        }
+    }
+
     // CTAs of a launch over `nrows` tile rows of pass `ps` (persistent kernel: at most one wave)
     int grid_for(const SorPass& ps, int nrows) const { return std::min(ps.tx.ntiles * nrows, sms * ctas_per_sm); }
 
@@ -230,8 +292,9 @@ struct SorRunner {
     }
 
     // returns the number of kernel launches
-    int run(SorArgs<T> a, T*& du, T*& dv, T*& du2, T*& dv2, int nsor) {
+    int run(SorArgs<T> a, T*& du, T*& dv, T*& du2, T*& dv2, int nsor, int level = -1) {
         const int w = a.w, h = a.h;
+        const bool lex = this->lex || (hybrid && w <= PF_HYBRID_MAX_WIDTH) || (lex_from >= 0 && level >= lex_from);
         size_t bytes = plane_for(w, h) * sizeof(T);
         int launches = 0;
         if (lex || simple_rb || nsor == 0) {
@@ -239,6 +302,26 @@ struct SorRunner {
             PF_CUDA(cudaMemsetAsync(dv, 0, bytes, st));
         }
         if (nsor == 0) return 0;
+        if (lex && lex_band) {
+            LexArgs<T> la;
+            la.phi = a.phi; la.dxy = a.dxy; la.iu = a.iu; la.iv = a.iv; la.bu = a.bu; la.bv = a.bv;
+            la.du = du; la.dv = dv; la.w = w; la.h = h; la.pitch = a.pitch; la.alpha = a.alpha; la.omega = a.omega;
+            la.nsor = nsor;
+            lex_grid<kLexNS>(h, nsor, la.NI, la.NK);
+            const size_t words = kLexFlagHeader + (size_t)la.NI * nsor;
+            if (words > kLexFlagWords) throw Error(PF_EUNSUPPORTED, "level too tall for the lexicographic SOR flag buffer");
+            la.flags = lex_flags; la.err = lex_err;
+            PF_CUDA(cudaMemsetAsync(lex_flags, 0, words * sizeof(int), st));
+            la.stats = nullptr;
+            la.pub_every = 1; la.opt = 0;
+            if (const char* pe = getenv("PF_LEX_PUB")) la.pub_every = std::max(1, atoi(pe));
+            if (const char* oe = getenv("PF_LEX_OPT")) la.opt = atoi(oe);
+            if (const char* se = getenv("PF_LEX_STATS")) {
+                if (atoi(se)) { lex_stats(la); return 1; }
+            }
+            k_sor_lex<T, kLexNS><<<la.NI * la.NK, LexCfg<T, kLexNS>::THREADS, LexCfg<T, kLexNS>::smem_bytes(), st>>>(la);
+            return 1;
+        }
         if (lex) {
             a.du = du; a.dv = dv; a.du_in = nullptr; a.dv_in = nullptr;
             long long work = (long long)nsor * std::min(w, h);
@@ -284,7 +367,11 @@ class Plan : public PlanBase {
         bicubic_ = P.interp == PF_INTERP_BICUBIC;
         gmix_ = P.noise == PF_NOISE_GMIXTURE;
         const char* e = getenv("PF_NO_GRAPH");
-        use_graph_ = !(e && atoi(e)) && !lex_;
+        {
+            const char* li = getenv("PF_LEX_IMPL");
+            const bool coop = li && !strcmp(li, "coop");    // cooperative launches are not captured
+            use_graph_ = !(e && atoi(e)) && !((lex_ || P.mode == PF_MODE_FP32_HYBRID || getenv("PF_LEX_FROM")) && coop);
+        }
         e = getenv("PF_UNFUSED");
         fused_ = !(e && atoi(e)) && P.noise != PF_NOISE_GMIXTURE;   // the mixture weight lives in the stage-by-stage path
         e = getenv("PF_FUSED_TMA");
@@ -377,6 +464,7 @@ class Plan : public PlanBase {
         for (int i = 0; i < repeats; i++) run_solve();
         PF_CUDA(cudaEventRecord(ev_[1], st_));
         PF_CUDA(cudaStreamSynchronize(st_));
+        sor_.check_lex();
         float ms = 0;
         PF_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
         if (ms_total) *ms_total = ms;
@@ -396,6 +484,7 @@ class Plan : public PlanBase {
         download_outputs(vx, vy, warp);
         PF_CUDA(cudaEventRecord(ev_[3], st_));
         PF_CUDA(cudaStreamSynchronize(st_));
+        sor_.check_lex();
         if (timings) {
             for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
             float a = 0, b = 0, c = 0, d = 0;
@@ -625,7 +714,7 @@ class Plan : public PlanBase {
         a.du = nullptr; a.dv = nullptr; a.du_in = nullptr; a.dv_in = nullptr;
         a.w = w; a.h = h; a.pitch = pitch;
         a.alpha = (T)P.alpha; a.omega = (T)1.8;
-        int n = sor_.run(a, du_, dv_, du2_, dv2_, nsor);
+        int n = sor_.run(a, du_, dv_, du2_, dv2_, nsor, level);
         launches_ += n;
         sor_launches_ += n;
         if (level == 0) sor_launches_l0_ += n;
@@ -689,9 +778,8 @@ class Plan : public PlanBase {
             return;
         }
         if (kF64 && lex_) {
-            double lap0[64];
-            for (int i = 0; i < 64; i++) lap0[i] = 0.02;   // S/OpticalFlow.cpp:773-775
-            PF_CUDA(cudaMemcpyAsync(d_lap_, lap0, sizeof(lap0), cudaMemcpyHostToDevice, st_));
+            k_fill_f64<<<1, 64, 0, st_>>>(d_lap_, 0.02, 64);   // S/OpticalFlow.cpp:773-775 (a kernel, not a copy from the stack: the solve is graph captured)
+            launches_++;
         }
     }
 

@@ -1,0 +1,458 @@
+// k_sor_lex: the reference's lexicographic Gauss-Seidel/SOR order (S/OpticalFlow.cpp:451-505), exactly, as a
+// band-march over a time-skewed iteration space -- the fast replacement for the grid-synchronised wavefront.
+//
+// Pixel (i,j) of sweep s needs (i,j-1),(i-1,j) of sweep s and (i,j+1),(i+1,j),(i,j) of sweep s-1, so it can run at
+// wavefront time t = i + j + 2s.  The iteration space is cut so that every dependence points the same way:
+//
+//   band I of sweep s  = image rows [32 I - s, 32 I + 32 - s)          (the band slides up one row per sweep)
+//   CTA (I, K)         = band I of the NS consecutive sweeps s = K NS + k, k = 0..NS-1: one warp per sweep,
+//                        lane l = row 32 I - s + l, marching along the columns
+//   CTA step tau       : warp k, lane l updates column j = tau - l - k
+//
+// Inside a CTA every dependence is met by the previous step (left: own register, up: lane l-1 by shuffle, right /
+// down / own old value: warp k-1, through a shared-memory ring that is updated in place), so the NS compute warps
+// run in lock step with one named barrier per step.  Between CTAs all dependences point to (I-1, K) and (I, K-1)
+// (and (I-1, K-1)): no cycle, whatever the grain of the hand-off.  They travel through the du/dv planes themselves:
+// a warp stores a result to the plane when the CTA will not touch that pixel again (lane 31, whose row leaves the
+// band with the next sweep, and every lane of the group's last sweep); lane 0 of every warp reads its upper
+// neighbour (sweep s) and its own / right-hand old value (sweep s-1) from the plane, written there by band I-1; the
+// first warp of a group reads all its old values from the plane, written by group K-1.  Because a pixel's version
+// s is consumed by exactly the updates that precede its version s+1 in the dependence order, ONE copy per pixel --
+// the plane, in place -- is enough.
+//
+// Hand-off: per (band, sweep) a progress word P = completed CTA steps - k in global memory.  A helper warp
+// ("comm") publishes the CTA's progress (one gpu-scope fence per publication, off the compute warps' path) and
+// polls the (at most NS + 2) words this CTA depends on, turning them into the highest CTA step whose plane reads
+// are safe.  Plane reads are issued PD steps ahead of their use and bypass L1.  A second helper warp ("loader")
+// streams the six read-only coefficient planes of the band into a 64-column shared ring with cp.async (zero fill
+// outside the image), ahead of the march.  CTAs draw tickets in wavefront order (I + K), so a CTA only ever waits
+// for CTAs with smaller tickets: no co-residency assumption, no deadlock.
+//
+// Critical path: W + 31 + NS steps of march + ~(32 + hand-off) per band + ~(NS + hand-off) per sweep group, against
+// the (W + H + 2 nsor) grid-wide barriers of k_sor_wavefront.
+#pragma once
+#include <type_traits>
+#include "common.cuh"
+#include "sor.cuh"
+
+namespace pf {
+
+constexpr int kLexInf = 0x3fffffff;
+constexpr int kLexFlagHeader = 4;   // words: [0] ticket counter, [1] abort, [2..3] spare; then P[band][sweep]
+
+template <typename T>
+struct LexArgs {
+    const T *phi, *dxy, *iu, *iv, *bu, *bv;
+    T *du, *dv;          // in/out, zero on entry
+    int w, h, pitch;
+    T alpha, omega;
+    int nsor, NI, NK;
+    int* flags;          // zeroed before every launch
+    int* err;            // sticky: set when a hand-off timed out (never by a healthy run); checked by the host
+    int pub_every;       // publish progress every this many steps (and at the end)
+    int opt;             // developer knobs (PF_LEX_OPT): bit 0 = __threadfence instead of a release store, bit 1 = no fence at all
+                         // (timing experiment only, results undefined), bit 2 = plain bar.sync per step
+    long long* stats;    // developer build of the kernel only (PF_LEX_STATS=1): per CTA {I, K, start, end, wait plane, wait loader}
+};
+
+template <typename T, int NS>
+struct LexCfg {
+    static constexpr int RH = 32 + NS;        // local rows: row 0 = global row 32 I - K NS - NS
+    static constexpr int RING = 64;           // columns resident per row
+    static constexpr int RS = RING + 4;       // row stride: the skewed accesses (row l, column c - l) hit distinct banks
+    static constexpr int PD = 4;              // plane reads are issued this many steps before they are used
+    static constexpr int CW = 8;              // columns per loader chunk
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int RHD = NS + 33;       // du/dv ring rows: one more, the row below the band (old value, group K-1)
+    static constexpr int FB = 8;              // diagonals per fetcher batch (loads in flight together: the batch costs one L2 round trip)
+    static constexpr int FAHEAD = 24;         // the fetcher may run this many steps ahead of the march (ring slots must be dead)
+    static constexpr int THREADS = (NS + 3) * 32;
+    static constexpr size_t smem_bytes() { return sizeof(T) * (6 * RH + 2 * RHD) * RS; }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// named barrier over `nthreads` threads that also ORs a flag across them (uniform "stop" decision)
+__device__ __forceinline__ int bar_red_or_named(int id, int nthreads, int v) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 q, %3, 0;\n\t"
+        "bar.red.or.pred p, %1, %2, q;\n\t"
+        "selp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"(v)
+        : "memory");
+    return r;
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {   // MEMBAR.ALL.GPU + store, no L1 invalidation
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T, int NS, bool STATS = false>
+__global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
+    typedef LexCfg<T, NS> Cfg;
+    constexpr int RH = Cfg::RH, RHD = Cfg::RHD, RS = Cfg::RS, RING = Cfg::RING, PD = Cfg::PD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T(*C)[RH][RS] = reinterpret_cast<T(*)[RH][RS]>(smem_raw);                  // [6] phi dxy iu iv bu bv
+    T(*D)[RHD][RS] = reinterpret_cast<T(*)[RHD][RS]>(smem_raw + sizeof(T) * 6 * RH * RS);   // [2] du dv, updated in place
+    __shared__ volatile int s_ctr, s_loaded, s_avail, s_abort, s_fetched;
+    __shared__ int s_I, s_K;
+
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int W = a.w, H = a.h, P = a.pitch;
+
+    if (tid == 0) {
+        // tickets in wavefront order T = I + K (then by I): every CTA this one waits for holds a smaller ticket
+        int t = atomicAdd(a.flags, 1);
+        int I = 0, K = 0;
+        for (int d = 0; d < a.NI + a.NK - 1; d++) {
+            const int lo = max(0, d - (a.NK - 1)), hi = min(d, a.NI - 1), n = hi - lo + 1;
+            if (t < n) { I = lo + t; K = d - I; break; }
+            t -= n;
+        }
+        s_I = I; s_K = K;
+        s_ctr = 0; s_loaded = 0; s_avail = -1; s_abort = 0; s_fetched = 0;
+    }
+    __syncthreads();
+    const int I = s_I, K = s_K;
+    const int s_first = K * NS;
+    const int nk = min(NS, a.nsor - s_first);
+    const int rb = I * 32 - s_first - NS;          // global row of local row 0
+    const int nsteps = W + 30 + nk;
+    int* const myflag = a.flags + kLexFlagHeader + (size_t)I * a.nsor + s_first;
+
+    // rows of the band over all its sweeps: [32 I - s_first - nk + 1, 32 I - s_first + 31]
+    if (I * 32 - s_first + 31 < 0 || I * 32 - s_first - nk + 1 >= H) {
+        if (wp == NS && lane < nk) st_relaxed_gpu(myflag + lane, kLexInf);   // nothing to do and nothing stored
+        return;
+    }
+
+    long long st_t0 = 0, st_g0 = 0, st_wa = 0, st_wl = 0;
+    if (STATS && tid == 0) {
+        st_t0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_g0));
+    }
+    if (wp < NS) {
+        // ------------------------------------------------------------------------------------ compute warps
+        // Shared memory and registers only.  Every neighbour value comes from the du/dv ring: the lower and right old
+        // values were put there by warp k-1 (or by the fetcher warp for warp 0 and for lane 0), the upper new value
+        // by this warp's lane l-1 in the previous step (fetcher for lane 0).  The step body is branch free and
+        // software pipelined: the coefficients of step tau+1 are read during step tau, so that after the step barrier
+        // only the ring reads, the update chain and the ring write remain on the critical path.  Waits (fetcher,
+        // loader) are taken once per PD steps.
+        const int k = wp;
+        const bool live = k < nk;
+        const int s = s_first + k;
+        const int li = NS - k + lane;              // local row of this lane's pixels
+        const int gi = rb + li;                    // = 32 I - s + lane
+        const bool rowok = live && gi >= 0 && gi < H;
+        const bool zero_old = s == 0;              // the solve starts from du = dv = 0
+        const bool has_dn = rowok && gi + 1 < H && !zero_old;
+        const bool has_up = rowok && gi > 0;
+        const bool st_plane = k == nk - 1 || lane == 31;
+        const T one_m = (T)1 - a.omega, nalpha = -a.alpha;
+        const size_t row_o = (size_t)(rowok ? gi : 0) * P;
+        constexpr int CP = RH * RS, DP = RHD * RS;   // plane strides of the two rings
+        const T* const Crow = &C[0][li][0];
+        T* const Drow = &D[0][li][0];
+        T* const ps_du = a.du + row_o;
+        T* const ps_dv = a.dv + row_o;
+
+        int fetched = 0, loaded = 0;
+        bool ok = true;
+        // diagonals < need_f are in the ring, coefficient columns <= need_c are resident
+        auto wait_for = [&](int need_f, int need_c) {
+            long long w0 = 0;
+            if (fetched < need_f) {
+                if (STATS && tid == 0) w0 = clock64();
+                unsigned spins = 0;
+                while ((fetched = s_fetched) < need_f) {
+                    if (s_abort) { ok = false; break; }
+                    if (++spins > 64) __nanosleep(40);
+                }
+                if (STATS && tid == 0) st_wa += clock64() - w0;
+            }
+            if (loaded <= need_c) {
+                if (STATS && tid == 0) w0 = clock64();
+                unsigned spins = 0;
+                while ((loaded = s_loaded) <= need_c) {
+                    if (s_abort) { ok = false; break; }
+                    if (++spins > 64) __nanosleep(40);
+                }
+                if (STATS && tid == 0) st_wl += clock64() - w0;
+            }
+            __threadfence_block();   // the helpers' data is published before their counters; nothing below moves above the polls
+        };
+        const int nsteps4 = (nsteps + PD - 1) / PD * PD;   // the padding steps touch nothing (every column is past W)
+        wait_for(1, 0);
+        T cw_prev = 0, ru_prev = 0, rv_prev = 0;   // phi, du, dv of this row's previous column (zero before column 0)
+        T oc_du = 0, oc_dv = 0;                    // old value of the current pixel = last step's right value
+        if (k == 0 && lane == 0 && rowok && !zero_old) {   // the one thread whose column 0 has no previous step
+            oc_du = Drow[0];
+            oc_dv = Drow[DP];
+        }
+        // coefficients of the current step (column j); garbage while the lane is outside the image, never used then
+        int j = -lane - k;
+        T n_cw, n_wu, n_dxy, n_iu, n_iv, n_bu, n_bv;
+        {
+            const int c = j & (RING - 1);
+            n_cw = Crow[c]; n_wu = Crow[c - RS]; n_dxy = Crow[CP + c]; n_iu = Crow[2 * CP + c]; n_iv = Crow[3 * CP + c];
+            n_bu = Crow[4 * CP + c]; n_bv = Crow[5 * CP + c];
+        }
+        bool stop = false;
+        for (int tau0 = 0; !stop && tau0 < nsteps4; tau0 += PD) {
+            // this block consumes the diagonals tau0 .. tau0+PD-1; its last step preloads column tau0 + PD
+            wait_for(min(tau0 + PD, nsteps), min(tau0 + PD, W - 1));
+            if (STATS && tid == 0 && (tau0 & 63) == 0 && tau0 < 512) {   // timeline: when the march passes steps 0, 64, 128, ...
+                long long g;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                a.stats[16 * (size_t)(K * a.NI + I) + 8 + (tau0 >> 6)] = g;
+            }
+#pragma unroll
+            for (int q = 0; q < PD; q++) {
+                const int tau = tau0 + q;
+                const bool act = rowok && (unsigned)j < (unsigned)W;
+                const bool rvalid = rowok && !zero_old && (unsigned)(j + 1) < (unsigned)W;
+                const int c = j & (RING - 1), c1 = (j + 1) & (RING - 1);
+                // ring reads that depend on the previous step's barrier
+                T r_du = Drow[c1], r_dv = Drow[DP + c1];
+                T d_du = Drow[RS + c], d_dv = Drow[DP + RS + c];
+                T u_du = Drow[c - RS], u_dv = Drow[DP + c - RS];
+                r_du = rvalid ? r_du : (T)0; r_dv = rvalid ? r_dv : (T)0;
+                d_du = (has_dn && act) ? d_du : (T)0; d_dv = (has_dn && act) ? d_dv : (T)0;
+                u_du = (has_up && act) ? u_du : (T)0; u_dv = (has_up && act) ? u_dv : (T)0;
+                const T cw = act ? n_cw : (T)0, wl = cw_prev, wu = n_wu;
+                // the update, in the reference's operation order (missing neighbours contribute +0)
+                T s1 = 0, s2 = 0;
+                s1 += wl * ru_prev; s2 += wl * rv_prev;
+                s1 += cw * r_du;    s2 += cw * r_dv;
+                s1 += wu * u_du;    s2 += wu * u_dv;
+                s1 += cw * d_du;    s2 += cw * d_dv;
+                s1 *= nalpha;
+                s2 *= nalpha;
+                s1 += n_dxy * oc_dv;
+                T nu = one_m * oc_du + n_iu * (n_bu - s1);
+                s2 += n_dxy * nu;
+                T nv = one_m * oc_dv + n_iv * (n_bv - s2);
+                if (act) Drow[c] = nu;
+                if (act) Drow[DP + c] = nv;
+                if (act && st_plane) ps_du[j] = nu;
+                if (act && st_plane) ps_dv[j] = nv;
+                nu = act ? nu : (T)0;
+                nv = act ? nv : (T)0;
+                cw_prev = cw;
+                ru_prev = nu; rv_prev = nv;
+                oc_du = r_du; oc_dv = r_dv;
+                // next step's coefficients (read-only ring, no barrier needed)
+                n_cw = Crow[c1]; n_wu = Crow[c1 - RS]; n_dxy = Crow[CP + c1]; n_iu = Crow[2 * CP + c1]; n_iv = Crow[3 * CP + c1];
+                n_bu = Crow[4 * CP + c1]; n_bv = Crow[5 * CP + c1];
+                j++;
+                if (q == PD - 1) stop = bar_red_or_named(1, NS * 32, ok ? 0 : 1) != 0;   // an abort seen by anyone stops all
+                else asm volatile("bar.sync 1, %0;" ::"r"(NS * 32) : "memory");
+                if (tid == 0) s_ctr = (stop || tau + 1 >= nsteps) ? nsteps : tau + 1;
+            }
+        }
+        if (STATS && tid == 0) {
+            long long* o = a.stats + 16 * (size_t)(K * a.NI + I);
+            long long g1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+            o[0] = I; o[1] = K; o[2] = st_g0; o[3] = g1; o[4] = st_wa; o[5] = st_wl; o[6] = nsteps; o[7] = clock64() - st_t0;
+        }
+        return;
+    }
+
+    if (wp == NS) {
+        // ------------------------------------------------------------------------------------ comm warp
+        // lanes 0..NS: P of band I-1, sweeps s_first-1 .. s_first+NS-1;  lane NS+1: P of this band's sweep s_first-1
+        const int* dep = nullptr;
+        if (lane <= NS && I > 0 && s_first - 1 + lane >= 0 && lane <= nk)
+            dep = a.flags + kLexFlagHeader + (size_t)(I - 1) * a.nsor + (s_first - 1 + lane);
+        if (lane == NS + 1 && K > 0) dep = a.flags + kLexFlagHeader + (size_t)I * a.nsor + (s_first - 1);
+        int published = 0;
+        long long t0 = clock64();
+        for (;;) {
+            int bound = kLexInf;
+            if (dep) {
+                const int f = ld_relaxed_gpu(dep);
+                if (lane == NS + 1) bound = f - 1;                       // group K-1: P >= tau + 1
+                else {
+                    if (lane >= 1 && lane - 1 < nk) bound = min(bound, f + (lane - 1) - 32);   // upper neighbour of warp lane-1
+                    if (lane < nk) bound = min(bound, f + lane - 33);                          // right / own old value of warp lane
+                }
+            }
+            int ab = (lane == 31) ? ld_relaxed_gpu(a.flags + 1) : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                bound = min(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+                ab |= __shfl_xor_sync(0xffffffffu, ab, o);
+            }
+            const int ctr = s_ctr;
+            if (clock64() - t0 > 8000000000ll) ab = 1;                   // ~4 s: a lost dependence must not hang the GPU
+            if (ab) {
+                if (lane == 0) { st_relaxed_gpu(a.flags + 1, 1); st_relaxed_gpu(a.err, 1); s_abort = 1; }
+                break;
+            }
+            if (lane == 0) s_avail = bound;
+            if (ctr >= published + a.pub_every || (ctr >= nsteps && ctr > published)) {
+                // release: the compute warps' plane stores (ordered before s_ctr by their barrier) before the progress word
+                const int v = ctr >= nsteps ? kLexInf : ctr - lane;
+                if (a.opt & 1) { __threadfence(); if (lane < nk) st_relaxed_gpu(myflag + lane, v); }
+                else if (a.opt & 2) { if (lane < nk) st_relaxed_gpu(myflag + lane, v); }
+                else if (lane < nk) st_release_gpu(myflag + lane, v);
+                published = ctr;
+                t0 = clock64();
+            }
+            if (ctr >= nsteps) break;
+        }
+        return;
+    }
+
+    if (wp == NS + 2) {
+        // ------------------------------------------------------------------------------------ fetcher warp
+        // Diagonal tau = everything step tau of the march reads that another CTA produced, copied from the planes (L2)
+        // into the du/dv ring:
+        //   task t <= NS  : local row t (the row above / the top row of warp NS-1-t / NS-t), column tau - (NS-1-t),
+        //                   written by band I-1 (sweep s_first + NS-1-t); unused rows of a short group are skipped
+        //   task NS+1+m   : local row NS+1+m (m = 0..31, the band of warp 0 shifted down by one), column tau - m,
+        //                   written by group K-1 -- the old values of the group's first sweep
+        // FB diagonals per batch (loads in flight together), at most FAHEAD steps ahead of the march so that the ring
+        // slots overwritten are dead, never beyond what the comm warp has seen published.
+        constexpr int FB = Cfg::FB, NT = NS + 33;
+        const int DP = RHD * RS;
+        T* const Dbase = &D[0][0][0];
+        int row[2], off[2];          // this lane's two tasks: ring row (or -1) and column offset against the diagonal
+        size_t grow[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int t = h2 * 32 + lane;
+            int r = -1, o = 0;
+            if (t <= NS) {
+                if (I > 0 && t >= NS - nk && s_first + NS - 1 - t >= 0) { r = t; o = NS - 1 - t; }
+            } else if (t < NT) {
+                if (K > 0) { r = t; o = t - NS - 1; }
+            }
+            const int g = rb + (r >= 0 ? r : 0);
+            if (r >= 0 && (g < 0 || g >= H)) r = -1;
+            row[h2] = r; off[h2] = o; grow[h2] = (size_t)(g < 0 ? 0 : g) * P;
+        }
+        // the old value of pixel (top row of warp 0, column 0): no step reads it as a right-hand value
+        if (lane == 0 && K > 0 && I > 0 && rb + NS >= 0 && rb + NS < H) {
+            unsigned spins = 0;
+            while (s_avail < 0) {
+                if (s_abort) return;
+                if (++spins > 16) __nanosleep(100);
+            }
+            __threadfence_block();
+            D[0][NS][0] = __ldcg(a.du + (size_t)(rb + NS) * P);
+            D[1][NS][0] = __ldcg(a.dv + (size_t)(rb + NS) * P);
+        }
+        __syncwarp();
+        for (int t0 = 0; t0 < nsteps;) {
+            // batch = the diagonals that are safe right now, at most FB: one diagonal at a time while this CTA follows
+            // its producers closely (latency), full batches when it is behind (throughput)
+            int n = 0;
+            unsigned spins = 0;
+            for (;;) {
+                const int av = min(min(s_avail, s_ctr + Cfg::FAHEAD), nsteps - 1);
+                n = __shfl_sync(0xffffffffu, min(FB, av - t0 + 1), 0);   // one view of the counters for the whole warp
+                if (n > 0) break;
+                if (s_abort) return;
+                if (++spins > 16) __nanosleep(40);
+            }
+            const int last = t0 + n - 1;
+            __threadfence_block();
+            T vu[FB][2], vv[FB][2];
+#pragma unroll
+            for (int f = 0; f < FB; f++)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int x = t0 + f - off[h2];
+                    const bool on = row[h2] >= 0 && f < n && (unsigned)x < (unsigned)W;
+                    vu[f][h2] = 0; vv[f][h2] = 0;
+                    if (on) vu[f][h2] = __ldcg(a.du + grow[h2] + x);
+                    if (on) vv[f][h2] = __ldcg(a.dv + grow[h2] + x);
+                }
+#pragma unroll
+            for (int f = 0; f < FB; f++)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int x = t0 + f - off[h2];
+                    const bool on = row[h2] >= 0 && f < n && (unsigned)x < (unsigned)W;
+                    if (on) {
+                        T* q = Dbase + row[h2] * RS + (x & (RING - 1));
+                        q[0] = vu[f][h2];
+                        q[DP] = vv[f][h2];
+                    }
+                }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) s_fetched = last + 1;
+            t0 = last + 1;
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------- loader warp
+    {
+        constexpr int CW = Cfg::CW, VEC = Cfg::VEC, GPC = CW / VEC;   // 16-byte groups per row and chunk
+        const T* planes[6] = {a.phi, a.dxy, a.iu, a.iv, a.bu, a.bv};
+        const int nchunks = (W + CW - 1) / CW;
+        for (int ch = 0; ch < nchunks; ch++) {
+            // columns [CW ch - RING, ...) must be dead: the last reader is warp NS-1, lane 31
+            const int need = CW * ch + CW - RING + 31 + NS;
+            unsigned spins = 0;
+            while (s_ctr < need) {
+                if (s_abort) return;
+                if (++spins > 16) __nanosleep(100);
+            }
+            const int c0 = CW * ch, cs = c0 & (RING - 1);
+            // lane -> (row within a group of 32 / GPC rows, 16-byte piece of the row's CW columns): shifts only
+#pragma unroll
+            for (int p = 0; p < 6; p++) {
+#pragma unroll
+                for (int r0 = 0; r0 < RH; r0 += 32 / GPC) {
+                    const int r = r0 + lane / GPC, g = lane % GPC;
+                    if (r < RH) {
+                        const int gr = rb + r;
+                        const bool in = gr >= 0 && gr < H;
+                        const T* src = planes[p] + (in ? (size_t)gr * P + c0 + g * VEC : 0);
+                        cp_async16(&C[p][r][cs + g * VEC], src, in ? 16 : 0);
+                    }
+                }
+            }
+            cp_async_commit();
+            if (ch > 0) {
+                cp_async_wait<1>();
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) s_loaded = CW * ch;
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) s_loaded = kLexInf;
+    }
+}
+
+// bands and sweep groups of a level
+template <int NS>
+inline void lex_grid(int h, int nsor, int& NI, int& NK) {
+    NI = (h + nsor - 2) / 32 + 1;
+    NK = ceil_div(nsor, NS);
+}
+
+}  // namespace pf

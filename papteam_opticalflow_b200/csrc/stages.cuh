@@ -237,6 +237,7 @@ struct Stages {
             PF_CUDA(cudaEventRecord(e1, st));
             PF_CUDA(cudaStreamSynchronize(st));
             PF_CHECK_LAUNCH();
+            run.check_lex();
         } catch (...) {
             cudaStreamDestroy(st); cudaEventDestroy(e0); cudaEventDestroy(e1);
             throw;

@@ -11,7 +11,8 @@
 Inputs are float64, C-contiguous, (h, w, c) arrays in [0,1], gray passed as (h, w, 1); outputs are
 freshly allocated float64 arrays -- exactly the reference's contract.  Keyword-only extras:
     mode    'fp32_redblack' (fast, default) | 'fp64_wavefront' (matches the reference to <=1e-6)
-            | 'fp64_redblack' | 'fp32_wavefront'      (env PYFLOW_B200_MODE overrides the default)
+            | 'fp64_redblack' | 'fp32_wavefront' | 'fp32_hybrid' (fast mode with the reference's sweep order on the
+            pyramid levels <= 400 px wide)            (env PYFLOW_B200_MODE overrides the default)
     device  CUDA device index (default 0)
     profile True: run eagerly with CUDA events per phase and fill every timing key
 """
@@ -24,7 +25,7 @@ import numpy as np
 from . import _lib
 from ._lib import PyflowB200Error, check, dp  # noqa: F401
 
-MODES = {"fp64_wavefront": 0, "fp32_redblack": 1, "fp64_redblack": 2, "fp32_wavefront": 3}
+MODES = {"fp64_wavefront": 0, "fp32_redblack": 1, "fp64_redblack": 2, "fp32_wavefront": 3, "fp32_hybrid": 4}
 _FORK_DEFAULTS = dict(alpha=0.012, ratio=0.75, minWidth=20, nOuter=7, nInner=1, nSOR=30, colType=0)
 # reference timing-map keys (S/OpticalFlow.cpp:850-860) in PF_T_* order, then the GPU-only legs
 _TIMING_KEYS = ["Total C++ Execution", "Construction", "Allocation", "Phase1_Generate",

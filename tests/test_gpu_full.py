@@ -96,9 +96,48 @@ def test_config3_1920_fast_mode_full_frame():
 def test_config4_sequence_spot_checks(pair):
     """BASELINE config 4 / SURVEY 8d: parity spot checks on pairs 50 and 101 of the 1920-wide sequence (pair p =
     frames p -> p+1, Par/InputCreation/TestImagePairGenerator.py:151-171; pair 1 is the config-3 test), goldens
-    from the unmodified reference (tests/golden/make_golden_config4.py)."""
-    _fast_vs_parity_full_frame(load_frame(1920, pair), load_frame(1920, pair + 1), golden("hcm1920_p%d_L15_s8.npz" % pair),
-                               "1920 pair %d" % pair)
+    from the unmodified reference (tests/golden/make_golden_config4.py).
+
+    The parity mode matches the reference to 1e-6 as everywhere.  For the FP32 modes the mean-EPE clause holds, the
+    max-EPE clause (<= 0.5 px) CANNOT hold on these two pairs for any FP32 implementation, and the test pins down why
+    instead of loosening a number: both pairs contain vehicles moving 20-80 px between frames, far beyond what the
+    pyramid tracks, and there the reference's own result is chaotic --
+      * the reference's operation order and FP64 arithmetic, on an input perturbed by 1e-7 (40 000 times below the
+        1/255 quantisation of the frames), moves hundreds of pixels by more than 0.5 px (up to ~16 px);
+      * the reference's operation order in FP32 (fp32_wavefront: rounding is the ONLY difference) violates the clause
+        on as many pixels as the red-black fast mode, so the sweep order is not the cause and no faster-but-exact
+        ordering would cure it;
+      * every fast-mode outlier lies where the reference flow itself is large (occluded / untrackable motion)."""
+    a, b = load_frame(1920, pair), load_frame(1920, pair + 1)
+    g = golden("hcm1920_p%d_L15_s8.npz" % pair)
+    s = int(g["stride"])
+    _, px, py, pw = pyflow.coarse2fine_flow(a, b, 15, mode="fp64_wavefront")
+    assert np.abs(px[::s, ::s] - g["vx"]).max() <= 1e-6 and np.abs(py[::s, ::s] - g["vy"]).max() <= 1e-6
+    assert np.abs(pw[::s, ::s] - g["warpI2"]).max() <= 1e-6
+    assert np.allclose([px.sum(), py.sum(), pw.sum()], g["sums"], rtol=0, atol=1e-4)
+    out = {}
+    for mode in ("fp32_redblack", "fp32_wavefront", "fp32_hybrid"):
+        u, v, w2 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode=mode)
+        e = epe(u, v, px, py)                  # every pixel of the frame
+        d = np.abs(w2 - pw)
+        out[mode] = e
+        print("1920 pair %d %s, full frame: EPE mean %.5f p99 %.5f p99.9 %.4f max %.3f, %d px (%.4f%%) > 0.5 px | im2W mean %.2e"
+              % (pair, mode, e.mean(), np.quantile(e, 0.99), np.quantile(e, 0.999), e.max(), (e > 0.5).sum(), 100 * (e > 0.5).mean(), d.mean()))
+        assert e.mean() <= 0.02 and np.quantile(e, 0.99) <= 0.5 and (e > 0.5).mean() <= 3e-3
+        assert d.mean() <= 1e-3
+    rng = np.random.default_rng(0)
+    _, qx, qy, _ = pyflow.coarse2fine_flow(np.clip(a + 1e-7 * rng.standard_normal(a.shape), 0, 1), b, 15, mode="fp64_wavefront")
+    chaos = epe(qx, qy, px, py)
+    n_fast, n_lex32, n_ref = [(x > 0.5).sum() for x in (out["fp32_redblack"], out["fp32_wavefront"], chaos)]
+    print("1920 pair %d: reference order + FP64 on input + 1e-7 noise: max %.3f, %d px > 0.5 px; reference order in FP32: %d px; "
+          "red-black FP32: %d px" % (pair, chaos.max(), n_ref, n_lex32, n_fast))
+    assert n_ref >= 100 and chaos.max() > 5          # the reference's own answer is not determined to 0.5 px here
+    assert n_lex32 >= 100 and n_fast <= 1.5 * n_lex32   # FP32 rounding alone costs as much as rounding + red-black order
+    bad = out["fp32_redblack"] > 0.5
+    assert np.hypot(px, py)[bad].mean() >= 10        # and it happens where the motion is untrackable, nowhere else
+    calm = np.hypot(px, py) < 3                       # still / slowly moving scene content
+    print("1920 pair %d: %.1f%% of the frame moves < 3 px; there the fast mode is off by max %.3f px, %d px > 0.5 px (reference under 1e-7 noise: %d px)"
+          % (pair, 100 * calm.mean(), out["fp32_redblack"][calm].max(), (out["fp32_redblack"][calm] > 0.5).sum(), (chaos[calm] > 0.5).sum()))
 
 
 def test_config3_1920_parity_mode_subsampled_golden():
@@ -284,26 +323,31 @@ def test_config5_4k_gray_sor60_both_modes_vs_reference_golden():
     assert np.abs(w2[::s, ::s] - g["warpI2"]).max() <= 1e-6
     assert np.allclose([u.sum(), v.sum(), w2.sum()], g["sums"], rtol=0, atol=1e-3)
     pu, pv = u, v                                   # parity-mode flow == the reference, full resolution
-    u, v, w2 = pyflow.coarse2fine_flow(im1, im2, *args, mode="fp32_redblack")
-    e = epe(u, v, pu, pv)
-    d = np.abs(w2[::s, ::s] - g["warpI2"])
-    gt = np.hypot(u - gu, v - gv)
-    frac = (e > 0.5).mean()
-    print("4K fast mode: EPE vs reference mean %.5f p99.9 %.5f max %.3f, %.4f%% of pixels > 0.5 px | vs ground truth mean %.4f "
-          "(reference itself %.4f) | im2W mean %.2e" % (e.mean(), np.quantile(e, 0.999), e.max(), 100 * frac, gt.mean(),
-                                                       float(g["gt_epe_mean"]), d.mean()))
-    assert e.mean() <= 0.02 and np.quantile(e, 0.999) <= 0.5
-    assert d.mean() <= 1e-3
-    assert abs(gt.mean() - float(g["gt_epe_mean"])) < 0.01
-    # The max-EPE clause (<= 0.5 px) does NOT hold on this input: ~0.01 % of the pixels, all next to the
-    # image border where the flow points out of the frame and the reference itself is > 5 px from the
-    # ground truth, move by more than 0.5 px.  The cause is the red-black ORDERING, not FP32: the FP64
-    # red-black mode shows the same outliers, while FP32 arithmetic in the reference's lexicographic
-    # order stays within 0.2 px everywhere.
-    assert frac <= 2e-4
-    u64, v64, _ = pyflow.coarse2fine_flow(im1, im2, *args, mode="fp64_redblack")
-    e64 = epe(u64, v64, pu, pv)
-    assert abs((e64 > 0.5).mean() - frac) <= 5e-5 and abs(e64.mean() - e.mean()) <= 1e-4
+    gt = None
+    for mode in ("fp32_hybrid", "fp32_redblack"):
+        u, v, w2 = pyflow.coarse2fine_flow(im1, im2, *args, mode=mode)
+        e = epe(u, v, pu, pv)
+        d = np.abs(w2[::s, ::s] - g["warpI2"])
+        gt = np.hypot(u - gu, v - gv)
+        frac = (e > 0.5).mean()
+        print("4K %s: EPE vs reference mean %.5f p99.9 %.5f max %.3f, %.4f%% of pixels > 0.5 px | vs ground truth mean %.4f "
+              "(reference itself %.4f) | im2W mean %.2e" % (mode, e.mean(), np.quantile(e, 0.999), e.max(), 100 * frac, gt.mean(),
+                                                           float(g["gt_epe_mean"]), d.mean()))
+        assert e.mean() <= 0.02 and np.quantile(e, 0.999) <= 0.5
+        assert d.mean() <= 1e-3
+        assert abs(gt.mean() - float(g["gt_epe_mean"])) < 0.01
+        if mode == "fp32_hybrid":
+            # the fast mode with the reference's sweep order on the levels <= 400 px wide meets BOTH clauses on every pixel
+            assert e.max() <= 0.5
+        else:
+            # Pure red-black order: ~0.01 % of the pixels, all next to the image border where the flow points out of the
+            # frame (weak data term, the reference itself is > 5 px from the ground truth), move by more than 0.5 px.
+            # The cause is the ORDER on the coarse, under-iterated levels -- multiplied by 1/ratio per level on the way
+            # up -- not FP32: FP64 red-black shows the same outliers, the reference order in FP32 stays within 0.2 px.
+            assert frac <= 2e-4
+            u64, v64, _ = pyflow.coarse2fine_flow(im1, im2, *args, mode="fp64_redblack")
+            e64 = epe(u64, v64, pu, pv)
+            assert abs((e64 > 0.5).mean() - frac) <= 5e-5 and abs(e64.mean() - e.mean()) <= 1e-4
     ul, vl, _ = pyflow.coarse2fine_flow(im1, im2, *args, mode="fp32_wavefront")
     el = epe(ul, vl, pu, pv)
     assert el.mean() <= 1e-4 and el.max() <= 0.5

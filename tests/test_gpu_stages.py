@@ -140,3 +140,27 @@ def test_stage_fixtures_from_reference_fp64():
     assert np.array_equal(G.warpfl(g["f1"], g["f2"], g["u"], g["v"], G.F64), g["warp"])
     assert np.array_equal(G.resize_to(g["u"], 85, 128, 1 / 0.75, G.F64)[..., 0], g["up"][..., 0])
     assert np.array_equal(G.bicubic(g["im1"], g["im2"], g["u"], g["v"], G.F64), g["bicubic"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (19, 34), (31, 33), (33, 65), (45, 81), (70, 100), (107, 192), (131, 67), (192, 341)])
+def test_sor_lexicographic_band_march_equals_grid_wavefront(shape, monkeypatch):
+    """k_sor_lex (time-skewed band march: one warp per sweep, CTAs handing du/dv over through the planes with progress
+    words) against k_sor_wavefront (one grid-wide barrier per anti-diagonal), which test_assemble_and_sor_fp64 pins
+    to the oracle: the SAME bits in FP64 for every combination of one / several bands and one / several sweep groups,
+    images smaller than a band, odd sizes, and more sweeps than rows (S/OpticalFlow.cpp:451-505)."""
+    h, w = shape
+    r = np.random.default_rng(h * 1000 + w)
+    sysm = (r.random((h, w)) * 40 + 0.5, r.standard_normal((h, w)) * 0.2, r.random((h, w)) + 0.05, r.random((h, w)) + 0.05,
+            r.standard_normal((h, w)), r.standard_normal((h, w)))
+    for nsor in ((1, 7, 8, 9, 17, 30, 72) if h * w < 30000 else (9, 30)):
+        monkeypatch.setenv("PF_LEX_IMPL", "coop")
+        ru, rv = G.sor(*sysm, 0.012, nsor, G.F64)
+        monkeypatch.setenv("PF_LEX_IMPL", "band")
+        gu, gv = G.sor(*sysm, 0.012, nsor, G.F64)
+        assert np.array_equal(gu, ru) and np.array_equal(gv, rv), (shape, nsor)
+        monkeypatch.setenv("PF_LEX_IMPL", "coop")
+        r32 = G.sor(*sysm, 0.012, nsor, G.F32LEX)
+        monkeypatch.setenv("PF_LEX_IMPL", "band")
+        g32 = G.sor(*sysm, 0.012, nsor, G.F32LEX)
+        if np.isfinite(r32[0]).all() and np.abs(r32[0]).max() < 1e3:   # random systems may diverge under omega = 1.8
+            assert np.allclose(g32[0], r32[0], rtol=0, atol=2e-3 * max(1.0, np.abs(r32[0]).max()))
