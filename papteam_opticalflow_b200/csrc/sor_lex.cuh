@@ -67,7 +67,7 @@ struct LexCfg {
     static constexpr int FB = 8;              // diagonals per fetcher batch (loads in flight together: the batch costs one L2 round trip)
     static constexpr int FAHEAD = 24;         // the fetcher may run this many steps ahead of the march (ring slots must be dead)
     static constexpr int THREADS = (NS + 3) * 32;
-    static constexpr size_t smem_bytes() { return sizeof(T) * (6 * RH + 2 * RHD) * RS; }
+    static constexpr size_t smem_bytes() { return 2 * sizeof(T) * (3 * RH + RHD) * RS; }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -106,8 +106,11 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
     typedef LexCfg<T, NS> Cfg;
     constexpr int RH = Cfg::RH, RHD = Cfg::RHD, RS = Cfg::RS, RING = Cfg::RING, PD = Cfg::PD;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T(*C)[RH][RS] = reinterpret_cast<T(*)[RH][RS]>(smem_raw);                  // [6] phi dxy iu iv bu bv
-    T(*D)[RHD][RS] = reinterpret_cast<T(*)[RHD][RS]>(smem_raw + sizeof(T) * 6 * RH * RS);   // [2] du dv, updated in place
+    typedef typename Vec2<T>::type V2;
+    // coefficient rings as PAIRS, so that a pixel costs three 8/16-byte reads instead of six scalar ones:
+    // [0] = {phi, dxy}, [1] = {iu, iv}, [2] = {bu, bv}; and the {du, dv} ring, updated in place
+    V2(*C)[RH][RS] = reinterpret_cast<V2(*)[RH][RS]>(smem_raw);
+    V2(*D)[RS] = reinterpret_cast<V2(*)[RS]>(smem_raw + sizeof(V2) * 3 * RH * RS);
     __shared__ volatile int s_ctr, s_loaded, s_avail, s_abort, s_fetched;
     __shared__ int s_I, s_K;
 
@@ -162,14 +165,17 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
         const bool zero_old = s == 0;              // the solve starts from du = dv = 0
         const bool has_dn = rowok && gi + 1 < H && !zero_old;
         const bool has_up = rowok && gi > 0;
-        const bool st_plane = k == nk - 1 || lane == 31;
+        const bool st_plane = (k == nk - 1 || lane == 31) && !(a.opt & 8);   // opt bit 3: timing experiment without plane stores
         const T one_m = (T)1 - a.omega, nalpha = -a.alpha;
         const size_t row_o = (size_t)(rowok ? gi : 0) * P;
-        constexpr int CP = RH * RS, DP = RHD * RS;   // plane strides of the two rings
-        const T* const Crow = &C[0][li][0];
-        T* const Drow = &D[0][li][0];
+        constexpr int CP = RH * RS;   // stride between the coefficient pair arrays
+        const V2* const Crow = &C[0][li][0];
+        V2* const Drow = &D[li][0];
         T* const ps_du = a.du + row_o;
         T* const ps_dv = a.dv + row_o;
+        // every lane of the warp has a row, an upper and a lower neighbour, and an old value: with the columns inside the
+        // image too, a step needs no predicate at all (the fast body below)
+        const bool full_rows = __all_sync(0xffffffffu, rowok && gi > 0 && gi + 1 < H && !zero_old);
 
         int fetched = 0, loaded = 0;
         bool ok = true;
@@ -194,24 +200,55 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 }
                 if (STATS && tid == 0) st_wl += clock64() - w0;
             }
-            __threadfence_block();   // the helpers' data is published before their counters; nothing below moves above the polls
+            // The helpers publish their data before their counters (fence on their side); on this side shared-memory reads
+            // of one thread are served in order, so a compiler barrier is all that is needed -- a MEMBAR here would also
+            // wait for this thread's plane stores in flight (an L2 round trip per block of steps).
+            asm volatile("" ::: "memory");
         };
         const int nsteps4 = (nsteps + PD - 1) / PD * PD;   // the padding steps touch nothing (every column is past W)
         wait_for(1, 0);
         T cw_prev = 0, ru_prev = 0, rv_prev = 0;   // phi, du, dv of this row's previous column (zero before column 0)
         T oc_du = 0, oc_dv = 0;                    // old value of the current pixel = last step's right value
         if (k == 0 && lane == 0 && rowok && !zero_old) {   // the one thread whose column 0 has no previous step
-            oc_du = Drow[0];
-            oc_dv = Drow[DP];
+            const V2 t = Drow[0];
+            oc_du = t.x; oc_dv = t.y;
         }
         // coefficients of the current step (column j); garbage while the lane is outside the image, never used then
         int j = -lane - k;
-        T n_cw, n_wu, n_dxy, n_iu, n_iv, n_bu, n_bv;
+        V2 n_a, n_b, n_c;   // {phi, dxy}, {iu, iv}, {bu, bv}
+        T n_wu;
         {
             const int c = j & (RING - 1);
-            n_cw = Crow[c]; n_wu = Crow[c - RS]; n_dxy = Crow[CP + c]; n_iu = Crow[2 * CP + c]; n_iv = Crow[3 * CP + c];
-            n_bu = Crow[4 * CP + c]; n_bv = Crow[5 * CP + c];
+            n_a = Crow[c]; n_b = Crow[CP + c]; n_c = Crow[2 * CP + c]; n_wu = Crow[c - RS].x;
         }
+        // the update of one pixel, in the reference's operation order (missing neighbours contribute +0)
+        auto update = [&](T cw, T wl, T wu, V2 r, V2 u, V2 d, T& nu, T& nv) {
+            if constexpr (sizeof(T) == 4) {
+                // FP32 (no reference bits to match): everything that does not need this step's ring reads is folded
+                // beforehand, leaving four dependent operations for du and one more for dv (each dependent FMA costs ~8
+                // cycles with two lock-stepped warps per scheduler)
+                const T au = one_m * oc_du + n_b.x * (n_c.x - n_a.y * oc_dv);   // no ring value in here
+                const T av = one_m * oc_dv + n_b.y * n_c.y;
+                const T ku = n_b.x * a.alpha, kv = n_b.y * a.alpha;
+                const T l1 = wl * ru_prev, l2 = wl * rv_prev;
+                const T t1 = fmaf(wu, u.x, fmaf(cw, r.x + d.x, l1));
+                const T t2 = fmaf(wu, u.y, fmaf(cw, r.y + d.y, l2));
+                nu = fmaf(ku, t1, au);
+                nv = fmaf(-(n_b.y * n_a.y), nu, fmaf(kv, t2, av));
+                return;
+            }
+            T s1 = 0, s2 = 0;
+            s1 += wl * ru_prev; s2 += wl * rv_prev;
+            s1 += cw * r.x;     s2 += cw * r.y;
+            s1 += wu * u.x;     s2 += wu * u.y;
+            s1 += cw * d.x;     s2 += cw * d.y;
+            s1 *= nalpha;
+            s2 *= nalpha;
+            s1 += n_a.y * oc_dv;
+            nu = one_m * oc_du + n_b.x * (n_c.x - s1);
+            s2 += n_a.y * nu;
+            nv = one_m * oc_dv + n_b.y * (n_c.y - s2);
+        };
         bool stop = false;
         for (int tau0 = 0; !stop && tau0 < nsteps4; tau0 += PD) {
             // this block consumes the diagonals tau0 .. tau0+PD-1; its last step preloads column tau0 + PD
@@ -221,48 +258,62 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
                 a.stats[16 * (size_t)(K * a.NI + I) + 8 + (tau0 >> 6)] = g;
             }
+            // all 32 lanes inside the image with a right-hand neighbour for the whole block (lane 31 is the last to enter,
+            // lane 0 the first to reach the last column)?
+            const bool fast = full_rows && tau0 - 31 - k >= 0 && tau0 + PD - k < W;
+            if (fast) {
 #pragma unroll
-            for (int q = 0; q < PD; q++) {
-                const int tau = tau0 + q;
-                const bool act = rowok && (unsigned)j < (unsigned)W;
-                const bool rvalid = rowok && !zero_old && (unsigned)(j + 1) < (unsigned)W;
-                const int c = j & (RING - 1), c1 = (j + 1) & (RING - 1);
-                // ring reads that depend on the previous step's barrier
-                T r_du = Drow[c1], r_dv = Drow[DP + c1];
-                T d_du = Drow[RS + c], d_dv = Drow[DP + RS + c];
-                T u_du = Drow[c - RS], u_dv = Drow[DP + c - RS];
-                r_du = rvalid ? r_du : (T)0; r_dv = rvalid ? r_dv : (T)0;
-                d_du = (has_dn && act) ? d_du : (T)0; d_dv = (has_dn && act) ? d_dv : (T)0;
-                u_du = (has_up && act) ? u_du : (T)0; u_dv = (has_up && act) ? u_dv : (T)0;
-                const T cw = act ? n_cw : (T)0, wl = cw_prev, wu = n_wu;
-                // the update, in the reference's operation order (missing neighbours contribute +0)
-                T s1 = 0, s2 = 0;
-                s1 += wl * ru_prev; s2 += wl * rv_prev;
-                s1 += cw * r_du;    s2 += cw * r_dv;
-                s1 += wu * u_du;    s2 += wu * u_dv;
-                s1 += cw * d_du;    s2 += cw * d_dv;
-                s1 *= nalpha;
-                s2 *= nalpha;
-                s1 += n_dxy * oc_dv;
-                T nu = one_m * oc_du + n_iu * (n_bu - s1);
-                s2 += n_dxy * nu;
-                T nv = one_m * oc_dv + n_iv * (n_bv - s2);
-                if (act) Drow[c] = nu;
-                if (act) Drow[DP + c] = nv;
-                if (act && st_plane) ps_du[j] = nu;
-                if (act && st_plane) ps_dv[j] = nv;
-                nu = act ? nu : (T)0;
-                nv = act ? nv : (T)0;
-                cw_prev = cw;
-                ru_prev = nu; rv_prev = nv;
-                oc_du = r_du; oc_dv = r_dv;
-                // next step's coefficients (read-only ring, no barrier needed)
-                n_cw = Crow[c1]; n_wu = Crow[c1 - RS]; n_dxy = Crow[CP + c1]; n_iu = Crow[2 * CP + c1]; n_iv = Crow[3 * CP + c1];
-                n_bu = Crow[4 * CP + c1]; n_bv = Crow[5 * CP + c1];
-                j++;
-                if (q == PD - 1) stop = bar_red_or_named(1, NS * 32, ok ? 0 : 1) != 0;   // an abort seen by anyone stops all
-                else asm volatile("bar.sync 1, %0;" ::"r"(NS * 32) : "memory");
-                if (tid == 0) s_ctr = (stop || tau + 1 >= nsteps) ? nsteps : tau + 1;
+                for (int q = 0; q < PD; q++) {
+                    const int tau = tau0 + q;
+                    const int c = j & (RING - 1), c1 = (j + 1) & (RING - 1);
+                    const V2 r = Drow[c1], d = Drow[RS + c], u = Drow[c - RS];
+                    T nu, nv;
+                    update(n_a.x, cw_prev, n_wu, r, u, d, nu, nv);
+                    Drow[c] = V2{nu, nv};
+                    if (st_plane) { ps_du[j] = nu; ps_dv[j] = nv; }
+                    cw_prev = n_a.x;
+                    ru_prev = nu; rv_prev = nv;
+                    oc_du = r.x; oc_dv = r.y;
+                    n_a = Crow[c1]; n_b = Crow[CP + c1]; n_c = Crow[2 * CP + c1]; n_wu = Crow[c1 - RS].x;
+                    j++;
+                    if (q == PD - 1) {
+                        stop = bar_red_or_named(1, NS * 32, ok ? 0 : 1) != 0;   // an abort seen by anyone stops all
+                        // progress once per block: a store after every barrier costs ~50 cycles per step (tools/bar_micro.cu)
+                        if (tid == 0) s_ctr = (stop || tau + 1 >= nsteps) ? nsteps : tau + 1;
+                    } else {
+                        asm volatile("bar.sync 1, %0;" ::"r"(NS * 32) : "memory");
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PD; q++) {
+                    const int tau = tau0 + q;
+                    const bool act = rowok && (unsigned)j < (unsigned)W;
+                    const bool rvalid = rowok && !zero_old && (unsigned)(j + 1) < (unsigned)W;
+                    const int c = j & (RING - 1), c1 = (j + 1) & (RING - 1);
+                    V2 r = Drow[c1], d = Drow[RS + c], u = Drow[c - RS];
+                    if (!rvalid) r = V2{0, 0};
+                    if (!(has_dn && act)) d = V2{0, 0};
+                    if (!(has_up && act)) u = V2{0, 0};
+                    const T cw = act ? n_a.x : (T)0;
+                    T nu, nv;
+                    update(cw, cw_prev, n_wu, r, u, d, nu, nv);
+                    if (act) Drow[c] = V2{nu, nv};
+                    if (act && st_plane) { ps_du[j] = nu; ps_dv[j] = nv; }
+                    nu = act ? nu : (T)0;
+                    nv = act ? nv : (T)0;
+                    cw_prev = cw;
+                    ru_prev = nu; rv_prev = nv;
+                    oc_du = r.x; oc_dv = r.y;
+                    n_a = Crow[c1]; n_b = Crow[CP + c1]; n_c = Crow[2 * CP + c1]; n_wu = Crow[c1 - RS].x;
+                    j++;
+                    if (q == PD - 1) {
+                        stop = bar_red_or_named(1, NS * 32, ok ? 0 : 1) != 0;
+                        if (tid == 0) s_ctr = (stop || tau + 1 >= nsteps) ? nsteps : tau + 1;
+                    } else {
+                        asm volatile("bar.sync 1, %0;" ::"r"(NS * 32) : "memory");
+                    }
+                }
             }
         }
         if (STATS && tid == 0) {
@@ -331,8 +382,6 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
         // FB diagonals per batch (loads in flight together), at most FAHEAD steps ahead of the march so that the ring
         // slots overwritten are dead, never beyond what the comm warp has seen published.
         constexpr int FB = Cfg::FB, NT = NS + 33;
-        const int DP = RHD * RS;
-        T* const Dbase = &D[0][0][0];
         int row[2], off[2];          // this lane's two tasks: ring row (or -1) and column offset against the diagonal
         size_t grow[2];
 #pragma unroll
@@ -356,8 +405,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 if (++spins > 16) __nanosleep(100);
             }
             __threadfence_block();
-            D[0][NS][0] = __ldcg(a.du + (size_t)(rb + NS) * P);
-            D[1][NS][0] = __ldcg(a.dv + (size_t)(rb + NS) * P);
+            D[NS][0] = V2{__ldcg(a.du + (size_t)(rb + NS) * P), __ldcg(a.dv + (size_t)(rb + NS) * P)};
         }
         __syncwarp();
         for (int t0 = 0; t0 < nsteps;) {
@@ -391,11 +439,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 for (int h2 = 0; h2 < 2; h2++) {
                     const int x = t0 + f - off[h2];
                     const bool on = row[h2] >= 0 && f < n && (unsigned)x < (unsigned)W;
-                    if (on) {
-                        T* q = Dbase + row[h2] * RS + (x & (RING - 1));
-                        q[0] = vu[f][h2];
-                        q[DP] = vv[f][h2];
-                    }
+                    if (on) D[row[h2]][x & (RING - 1)] = V2{vu[f][h2], vv[f][h2]};
                 }
             __syncwarp();
             __threadfence_block();
@@ -406,10 +450,16 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
     }
 
     // ---------------------------------------------------------------------------------------- loader warp
+    // The six coefficient planes of the band, 8 columns at a time, ahead of the march: 16-byte loads per plane and row
+    // piece, interleaved pairwise in registers ({phi, dxy}, {iu, iv}, {bu, bv}) and stored as pairs; rows outside the image
+    // are zero ("phantom pixels": the missing upper neighbour of row 0 gets weight 0 without a test).
     {
-        constexpr int CW = Cfg::CW, VEC = Cfg::VEC, GPC = CW / VEC;   // 16-byte groups per row and chunk
+        constexpr int CW = Cfg::CW, VEC = Cfg::VEC, GPC = CW / VEC, RPI = 32 / GPC;   // pieces per row and chunk, rows per pass
+        constexpr int NIT = (RH + RPI - 1) / RPI;
+        typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type LV;   // 16 bytes
         const T* planes[6] = {a.phi, a.dxy, a.iu, a.iv, a.bu, a.bv};
         const int nchunks = (W + CW - 1) / CW;
+        const int g = lane % GPC, rsub = lane / GPC;
         for (int ch = 0; ch < nchunks; ch++) {
             // columns [CW ch - RING, ...) must be dead: the last reader is warp NS-1, lane 31
             const int need = CW * ch + CW - RING + 31 + NS;
@@ -419,32 +469,35 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 if (++spins > 16) __nanosleep(100);
             }
             const int c0 = CW * ch, cs = c0 & (RING - 1);
-            // lane -> (row within a group of 32 / GPC rows, 16-byte piece of the row's CW columns): shifts only
+            LV v[NIT][6];
 #pragma unroll
-            for (int p = 0; p < 6; p++) {
+            for (int it = 0; it < NIT; it++) {
+                const int r = it * RPI + rsub, gr = rb + r;
+                const bool in = r < RH && gr >= 0 && gr < H;
 #pragma unroll
-                for (int r0 = 0; r0 < RH; r0 += 32 / GPC) {
-                    const int r = r0 + lane / GPC, g = lane % GPC;
-                    if (r < RH) {
-                        const int gr = rb + r;
-                        const bool in = gr >= 0 && gr < H;
-                        const T* src = planes[p] + (in ? (size_t)gr * P + c0 + g * VEC : 0);
-                        cp_async16(&C[p][r][cs + g * VEC], src, in ? 16 : 0);
+                for (int p = 0; p < 6; p++) {
+                    if (in) v[it][p] = __ldg(reinterpret_cast<const LV*>(planes[p] + (size_t)gr * P + c0 + g * VEC));
+                    else v[it][p] = LV{};
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int r = it * RPI + rsub;
+                if (r < RH) {
+#pragma unroll
+                    for (int pp = 0; pp < 3; pp++) {
+                        const T* x = reinterpret_cast<const T*>(&v[it][2 * pp]);
+                        const T* y = reinterpret_cast<const T*>(&v[it][2 * pp + 1]);
+                        V2* dst = &C[pp][r][cs + g * VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) dst[e] = V2{x[e], y[e]};
                     }
                 }
             }
-            cp_async_commit();
-            if (ch > 0) {
-                cp_async_wait<1>();
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) s_loaded = CW * ch;
-            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) s_loaded = ch + 1 < nchunks ? CW * (ch + 1) : kLexInf;
         }
-        cp_async_wait<0>();
-        __syncwarp();
-        __threadfence_block();
-        if (lane == 0) s_loaded = kLexInf;
     }
 }
 
