@@ -133,7 +133,7 @@ struct SorRunner {
     static constexpr int kR = kF64 ? 2 : PF_SOR_R;
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, hybrid = false, simple_rb = false, use_tma = true;
+    bool lex = false, hybrid = false, simple_rb = false, use_tma = true, small_regions = false;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     int tune = PF_TUNE_THROUGHPUT;
     int lex_from = -1;   // experiment (PF_LEX_FROM=k): pyramid levels >= k use the lexicographic kernel in every mode
@@ -174,6 +174,9 @@ struct SorRunner {
             int per_sm = 1;
             PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_rb_tma<T, kR, kNW>, kNW * 32, bytes));
             ctas_per_sm = std::max(1, per_sm);
+            e = getenv("PF_SOR_SMALL");
+            small_regions = !kF64 && !(e && !atoi(e));
+            if (small_regions) { init_small<2, 16>(); init_small<4, 16>(); }
         }
         e = getenv("PF_LEX_IMPL");
         lex_band = !(e && !strcmp(e, "coop"));
@@ -191,6 +194,32 @@ struct SorRunner {
             PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_wavefront<T>, 256, 0));
             coop_max_blocks = std::max(1, per_sm * sms);
         }
+    }
+
+    // ---- levels that fit ONE region: the whole solve is one launch of one CTA, bound by the chain of half-sweeps.  With
+    //      R rows per thread a half-sweep is R dependent pixel updates; regions of 64 x 32 (R = 2) and 64 x 64 (R = 4) with
+    //      16 warps cut that chain to a quarter / half of the 64 x 64, R = 8, 8-warp region the large levels use (which
+    //      trades the longer chain for fewer, register-richer warps).  Same update, same bits.
+    template <int R, int NW>
+    static size_t small_smem_bytes() { return sizeof(SorStage<T, R, NW>) + sizeof(T) * 2 * 2 * NW * 2 * kSorRegionW + 128; }
+    template <int R, int NW>
+    void init_small() {
+        PF_CUDA(cudaFuncSetAttribute(k_sor_rb_tma<T, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes<R, NW>()));
+    }
+    template <int R, int NW>
+    void launch_single_region(const SorArgs<T>& a, T* du_out, T* dv_out, int nsor) {
+        constexpr int RH = R * NW;
+        SorMaps m;
+        m.phi = make_plane_map(a.phi, a.w, a.h, a.pitch, 72, RH + 1);
+        m.dxy = make_plane_map(a.dxy, a.w, a.h, a.pitch, kSorRegionW, RH);
+        m.iu = make_plane_map(a.iu, a.w, a.h, a.pitch, kSorRegionW, RH);
+        m.iv = make_plane_map(a.iv, a.w, a.h, a.pitch, kSorRegionW, RH);
+        m.bu = make_plane_map(a.bu, a.w, a.h, a.pitch, kSorRegionW, RH);
+        m.bv = make_plane_map(a.bv, a.w, a.h, a.pitch, kSorRegionW, RH);
+        m.du = make_plane_map(du_out, a.w, a.h, a.pitch, kSorRegionW, RH);   // not read: the solve starts from zero
+        m.dv = make_plane_map(dv_out, a.w, a.h, a.pitch, kSorRegionW, RH);
+        k_sor_rb_tma<T, R, NW><<<1, NW * 32, small_smem_bytes<R, NW>(), st>>>(m, du_out, dv_out, a.w, a.h, a.pitch, a.alpha, a.omega, nsor, 0, 1, 1,
+                                                                              kSorRegionW, RH, 0, SorPeer<T>());
     }
 
     // one launch of the tile kernel: sweeps fused, whether it reads du/dv, and its tiling
@@ -339,6 +368,15 @@ struct SorRunner {
                 }
             return launches;
         }
+        if (small_regions && use_tma && w <= kSorRegionW && h <= 64) {
+            if constexpr (!kF64) {
+                if (h <= 32) launch_single_region<2, 16>(a, du2, dv2, nsor);
+                else launch_single_region<4, 16>(a, du2, dv2, nsor);
+                std::swap(du, du2);
+                std::swap(dv, dv2);
+                return 1;
+            }
+        }
         for (const SorPass& ps : schedule(w, h, nsor)) {
             launch_pass(a, ps, du, dv, du2, dv2, 0, ps.ty.ntiles);
             launches++;
@@ -377,8 +415,12 @@ class Plan : public PlanBase {
         e = getenv("PF_FUSED_TMA");
         fused_tma_ = !(e && !atoi(e));
         if (fused_tma_)
+        {
             PF_CUDA(cudaFuncSetAttribute(k_fused_tma<T, kFTY, kFSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(FusedSmem<T, kFTY>) + 128)));
+            PF_CUDA(cudaFuncSetAttribute(k_fused_tma<T, kFTYs, kFSEGs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(FusedSmem<T, kFTYs>) + 128)));
+        }
         try {
             PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
             for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
@@ -852,10 +894,11 @@ class Plan : public PlanBase {
         set_phase(PF_T_PHASE1_GENERATE, k);
         filter_hv(c.f1, c.s1, c.g5, c.g5);
         if (fused_ && fused_tma_) {
-            c.fmaps.wf = make_image_map(c.wf.p, w, h, fc_, c.wf.pitch, c.wf.plane, 72, kFTY + 8);
-            c.fmaps.s1 = make_image_map(c.s1.p, w, h, fc_, c.s1.pitch, c.s1.plane, 72, kFTY + 4);
-            c.fmaps.u = make_plane_map(u_, w, h, pitch, 72, kFTY + 2);   // u_ / v_ are updated in place within a level
-            c.fmaps.v = make_plane_map(v_, w, h, pitch, 72, kFTY + 2);
+            const int ty = small_tiles(w, h) ? kFTYs : kFTY;
+            c.fmaps.wf = make_image_map(c.wf.p, w, h, fc_, c.wf.pitch, c.wf.plane, 72, ty + 8);
+            c.fmaps.s1 = make_image_map(c.s1.p, w, h, fc_, c.s1.pitch, c.s1.plane, 72, ty + 4);
+            c.fmaps.u = make_plane_map(u_, w, h, pitch, 72, ty + 2);   // u_ / v_ are updated in place within a level
+            c.fmaps.v = make_plane_map(v_, w, h, pitch, 72, ty + 2);
         }
         c.pw = w;
         c.ph = h;
@@ -891,8 +934,13 @@ class Plan : public PlanBase {
             fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = c.eps;
             fa.g5 = c.g5; fa.d5 = c.d5;
             if (fused_tma_) {
-                size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
-                k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
+                if (small_tiles(w, h)) {
+                    size_t smem = sizeof(FusedSmem<T, kFTYs>) + 128;
+                    k_fused_tma<T, kFTYs, kFSEGs><<<dim3(ceil_div(w, 64), ceil_div(h, kFTYs)), 64 * kFSEGs, smem, st_>>>(c.fmaps, fa);
+                } else {
+                    size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
+                    k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
+                }
             } else {
                 k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
             }
@@ -1104,6 +1152,15 @@ class Plan : public PlanBase {
 #define PF_FUSED_SEG 4
 #endif
     static constexpr int kFTX = 64, kFTY = kF64 ? 16 : PF_FUSED_TY, kFSEG = kF64 ? 8 : PF_FUSED_SEG;   // k_fused_* tile, 64*SEG threads
+    // Latency-tuned plans: levels whose 64x16 tiling leaves most SMs idle use 64x4 tiles instead.  A tile takes ~28 us
+    // whatever the level (five channels through three stencil stages, one after the other), so the coarse levels are
+    // bound by the latency of ONE tile; a 64x4 tile has half the rows to smooth (4+8 instead of 16+8) and a quarter of
+    // the centre rows.  More halo work in total, which is why throughput-tuned plans keep 64x16.  Same arithmetic per pixel.
+    static constexpr int kFTYs = kF64 ? 8 : 4, kFSEGs = kF64 ? 8 : 4;
+    bool small_tiles(int w, int h) const {
+        if (const char* e = getenv("PF_FUSED_SMALL")) return atoi(e) != 0 && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
+        return P.tune == PF_TUNE_LATENCY && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
+    }
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     bool bicubic_ = false, gmix_ = false;   // alternative solver branches
     int nlev_ = 0, fc_ = 0;
