@@ -187,7 +187,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 unsigned spins = 0;
                 while ((fetched = s_fetched) < need_f) {
                     if (s_abort) { ok = false; break; }
-                    if (++spins > 64) __nanosleep(40);
+                    if (++spins > 2) __nanosleep(64);   // waiting warps must not take issue slots from the helper they wait for
                 }
                 if (STATS && tid == 0) st_wa += clock64() - w0;
             }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 unsigned spins = 0;
                 while ((loaded = s_loaded) <= need_c) {
                     if (s_abort) { ok = false; break; }
-                    if (++spins > 64) __nanosleep(40);
+                    if (++spins > 2) __nanosleep(64);   // waiting warps must not take issue slots from the helper they wait for
                 }
                 if (STATS && tid == 0) st_wl += clock64() - w0;
             }
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
             unsigned spins = 0;
             while (s_avail < 0) {
                 if (s_abort) return;
-                if (++spins > 16) __nanosleep(100);
+                if (++spins > 1) __nanosleep(100);
             }
             __threadfence_block();
             D[NS][0] = V2{__ldcg(a.du + (size_t)(rb + NS) * P), __ldcg(a.dv + (size_t)(rb + NS) * P)};
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
                 n = __shfl_sync(0xffffffffu, min(FB, av - t0 + 1), 0);   // one view of the counters for the whole warp
                 if (n > 0) break;
                 if (s_abort) return;
-                if (++spins > 16) __nanosleep(40);
+                if (++spins > 1) __nanosleep(40);
             }
             const int last = t0 + n - 1;
             __threadfence_block();
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
             unsigned spins = 0;
             while (s_ctr < need) {
                 if (s_abort) return;
-                if (++spins > 16) __nanosleep(100);
+                if (++spins > 1) __nanosleep(100);
             }
             const int c0 = CW * ch, cs = c0 & (RING - 1);
             LV v[NIT][6];
