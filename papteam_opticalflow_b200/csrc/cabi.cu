@@ -102,6 +102,7 @@ void pool_release(pf_plan* pl) {
     std::lock_guard<std::mutex> g(g_pool_mu);
     for (auto& e : g_pool)
         if (e.plan == pl) {
+            pl->impl->set_blocking_wait(-1);   // back to the process default (batch / sequence workers switch to blocking waits)
             e.busy = false;
             e.stamp = ++g_pool_clock;
             return;
@@ -434,6 +435,7 @@ int pf_batch_flow(int npairs, double* const* vx, double* const* vy, double* cons
             int r = PF_OK;
             Params pp{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[d]};
             pf_plan* pl = pool_acquire(pp, r);
+            if (pl) pl->impl->set_blocking_wait(1);   // many waiting host threads per process: never spin
             // pair p belongs to device p % ndevices; workers of one device share its queue
             while (r == PF_OK) {
                 int k = next[(size_t)d].fetch_add(1);
@@ -501,6 +503,7 @@ static int sequence_flow(int format, int nframes, const unsigned char* const* fr
             int rc = PF_OK;
             Params pp{h, w, c, alpha, ratio, minWidth, levels, nOuter, nInner, nSOR, colType, mode, devices[wk % ndevices]};
             pf_plan* pl = pool_acquire(pp, rc);
+            if (pl) pl->impl->set_blocking_wait(1);
             if (rc == PF_OK) {
                 rc = guarded([&]() -> int {
                     pl->impl->seq_first(frames[p0]);

@@ -89,6 +89,35 @@ inline bool same_solver(const Params& a, const Params& b) {
            a.col_type == b.col_type && a.mode == b.mode && a.interp == b.interp && a.noise == b.noise && a.tune == b.tune;
 }
 
+// How host threads wait for the GPU.  cudaStreamSynchronize spins (one context per process => the driver's heuristic
+// chooses spinning); a node runs one process per GPU with several waiting host threads each (batch workers, stager
+// threads), and 8 ranks x 8 spinning workers on 32 cores starve the threads that have copies to issue.  Blocking waits
+// (an event created with cudaEventBlockingSync) cost a few tens of microseconds of wake-up latency per wait.
+//   PF_WAIT=spin | block | auto (default): auto blocks when several processes share the node (LOCAL_WORLD_SIZE > 1);
+//   batch / sequence workers always block.
+inline bool default_block_waits() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PF_WAIT");
+        if (e && !strcmp(e, "spin")) v = 0;
+        else if (e && !strcmp(e, "block")) v = 1;
+        else {
+            const char* lw = getenv("LOCAL_WORLD_SIZE");
+            v = (lw && atoi(lw) > 1) ? 1 : 0;
+        }
+    }
+    return v != 0;
+}
+// wait for everything enqueued on `st` so far without burning a core
+inline void stream_wait_blocking(cudaStream_t st) {
+    cudaEvent_t ev = nullptr;
+    PF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    PF_CUDA(e);
+}
+
 inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }
 inline bool mode_is_lex(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP32_WAVEFRONT; }
 // does a pyramid level of this width run its SOR solves in the reference's lexicographic order?

@@ -37,6 +37,7 @@ struct PlanBase {
     virtual void seq_next(const unsigned char* frame, void* out, int format) = 0;   // format: PF_SEQ_*
     virtual cudaStream_t stream() const = 0;
     virtual int device() const = 0;
+    virtual void set_blocking_wait(int block) = 0;   // 1 / 0, or -1 = the process default (common.cuh)
 };
 
 // ---- simple bump allocator over one cudaMalloc ---------------------------------------------------
@@ -442,6 +443,8 @@ class Plan : public PlanBase {
         if (graph_) cudaGraphDestroy(graph_);
         for (auto& s : spans_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
         for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
+        if (ev_block_) cudaEventDestroy(ev_block_);
+        ev_block_ = nullptr;
         if (st_) cudaStreamDestroy(st_);
         gexec_ = nullptr; graph_ = nullptr; st_ = nullptr;
         for (auto& gp : gexec_seq_) for (auto& g : gp) g = nullptr;
@@ -496,7 +499,7 @@ class Plan : public PlanBase {
     void download(double* vx, double* vy, double* warp) override {
         PF_CUDA(cudaSetDevice(P.device));
         download_outputs(vx, vy, warp);
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
     }
 
     // device-only solve, `repeats` times back to back, timed with events on the launching stream
@@ -505,7 +508,7 @@ class Plan : public PlanBase {
         PF_CUDA(cudaEventRecord(ev_[0], st_));
         for (int i = 0; i < repeats; i++) run_solve();
         PF_CUDA(cudaEventRecord(ev_[1], st_));
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
         sor_.check_lex();
         float ms = 0;
         PF_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
@@ -525,7 +528,7 @@ class Plan : public PlanBase {
         PF_CUDA(cudaEventRecord(ev_[2], st_));
         download_outputs(vx, vy, warp);
         PF_CUDA(cudaEventRecord(ev_[3], st_));
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
         sor_.check_lex();
         if (timings) {
             for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
@@ -555,7 +558,7 @@ class Plan : public PlanBase {
         enqueue_solve();
         set_phase(-1, 0);
         PF_CUDA(cudaEventRecord(ev_[1], st_));
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
         profiling_ = false;
         for (int i = 0; i < PF_NUM_TIMINGS; i++) timings[i] = 0;
         double sor_l0 = 0;
@@ -591,7 +594,7 @@ class Plan : public PlanBase {
         if (!gmix_) throw Error(PF_EINVAL, "plan was not created with the Gaussian-mixture noise model");
         PF_CUDA(cudaSetDevice(P.device));
         double host[GM_FIELDS * kGmStride];
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
         PF_CUDA(cudaMemcpy(host, d_gm_, sizeof(host), cudaMemcpyDeviceToHost));
         n = std::min(n, fc_);
         for (int k = 0; k < n; k++) {
@@ -608,6 +611,13 @@ class Plan : public PlanBase {
     }
     cudaStream_t stream() const override { return st_; }
     int device() const override { return P.device; }
+    void set_blocking_wait(int block) override { block_wait_ = block < 0 ? default_block_waits() : block != 0; }
+    void sync_stream() {
+        if (!block_wait_) { PF_CUDA(cudaStreamSynchronize(st_)); return; }
+        if (!ev_block_) PF_CUDA(cudaEventCreateWithFlags(&ev_block_, cudaEventBlockingSync | cudaEventDisableTiming));
+        PF_CUDA(cudaEventRecord(ev_block_, st_));
+        PF_CUDA(cudaEventSynchronize(ev_block_));
+    }
 
     // per-level phase times of the last profile() call: out[level][PF_NUM_TIMINGS]
     int level_timings(double* out, int max_levels) const override {
@@ -1089,7 +1099,7 @@ class Plan : public PlanBase {
             enqueue_seq_pair(format);
         }
         PF_CUDA(cudaMemcpyAsync(out, d_vx_, (size_t)P.h * P.w * seq_bytes_per_pixel(format), cudaMemcpyDeviceToHost, st_));
-        PF_CUDA(cudaStreamSynchronize(st_));
+        sync_stream();
     }
 
   private:
@@ -1169,6 +1179,8 @@ class Plan : public PlanBase {
     Arena arena_;
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_block_ = nullptr;                 // blocking-sync event of sync_stream()
+    bool block_wait_ = default_block_waits();
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t gexec_ = nullptr;
     static constexpr int kSeqFormats = 3;

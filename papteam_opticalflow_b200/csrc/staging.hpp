@@ -107,9 +107,9 @@ class HostStager {
         if (cudaSetDevice(dev_) != cudaSuccess) return;
         for (auto& w : workers_) {
             if (cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking) != cudaSuccess) return;
-            if (cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) != cudaSuccess) return;
+            if (cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return;
             for (int s = 0; s < 2; s++) {
-                if (cudaEventCreateWithFlags(&w.ev[s], cudaEventDisableTiming) != cudaSuccess) return;
+                if (cudaEventCreateWithFlags(&w.ev[s], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return;
                 if (cudaHostAlloc((void**)&w.slot[s], kChunk, cudaHostAllocPortable) != cudaSuccess) {
                     cudaGetLastError();
                     return;
@@ -125,7 +125,7 @@ class HostStager {
             // wait for the producer OUTSIDE the lock: with several host threads (batch workers) the stager must not be
             // held for the length of one pair's solve while other threads have frames to upload
             PF_CUDA(cudaSetDevice(dev_));
-            PF_CUDA(cudaStreamSynchronize(other));
+            stream_wait_blocking(other);   // stager threads and the caller must not spin while other threads have copies to issue
         }
         std::lock_guard<std::mutex> g(mu_);
         PF_CUDA(cudaSetDevice(dev_));
