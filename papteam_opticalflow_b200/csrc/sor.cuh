@@ -336,6 +336,15 @@ struct SorStage {
 #ifndef PF_SOR_MINB
 #define PF_SOR_MINB 1
 #endif
+// The stage is handed back to TMA in PF_SOR_GROUPS groups of planes ({phi,dxy} {iu,iv} {bu,bv} {du,dv} for 4), each with
+// its own mbarrier: as soon as every thread has pulled a group into registers the same planes of the NEXT tile are
+// requested, so the loads of a tile start while the rest of the previous one is still being unpacked and the unpacking of
+// a tile starts while its last planes are still in flight.  With one group (round 1) the whole stage was released at
+// once: the L2 -> SM stream (131 KB per tile, ~3.7 us per wave of 148 tiles) idled during the 0.75 us of unpacking and
+// 0.8 us of it stayed exposed after the sweeps.  1, 2 or 4.
+#ifndef PF_SOR_GROUPS
+#define PF_SOR_GROUPS 1
+#endif
 // developer ablation builds (tools/sor_ablation.sh): bit 0 = no sweeps, bit 1 = no write-back, bit 2 = no TMA loads
 #ifndef PF_SORX
 #define PF_SORX 0
@@ -363,33 +372,36 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
     // half-sweep suffices: [buffer][du|dv][warp][top|bottom][x]
     typedef T ExBuf[2][NW][2][kSorRegionW];
     ExBuf* ex = reinterpret_cast<ExBuf*>(smem_raw + sizeof(Stage));
-    __shared__ __align__(8) uint64_t full_bar;
+    constexpr int NG = PF_SOR_GROUPS, PPG = 8 / NG;
+    static_assert(NG == 1 || NG == 2 || NG == 4, "planes per group must divide 8 and keep du, dv together");
+    __shared__ __align__(8) uint64_t full_bar[NG];
 
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int HL = 2 * nsw;
     const int ntiles = ntx * nty;
-    const uint32_t stage_bytes = (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW + (has_input ? 7 : 5) * RH * kSorRegionW));
     const T one_m = (T)1 - omega;
 
-    auto issue = [&](int tile) {
+    // plane p (0 phi, 1 dxy, 2 iu, 3 iv, 4 bu, 5 bv, 6 du, 7 dv) travels in group p / PPG
+    auto issue_group = [&](int tile, int g) {
         if (PF_SORX & 4) return;
         const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
         const int rx0 = tx * step_x, ry0 = ty * step_y;
-        mbar_expect_tx(&full_bar, stage_bytes);
-        tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar);
-        tma_load_2d(&st.pl[0][0][0], &maps.dxy, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[1][0][0], &maps.iu, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[2][0][0], &maps.iv, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[3][0][0], &maps.bu, rx0, ry0, &full_bar);
-        tma_load_2d(&st.pl[4][0][0], &maps.bv, rx0, ry0, &full_bar);
-        if (has_input) {
-            tma_load_2d(&st.pl[5][0][0], &maps.du, rx0, ry0, &full_bar);
-            tma_load_2d(&st.pl[6][0][0], &maps.dv, rx0, ry0, &full_bar);
+        const int p_lo = g * PPG, p_hi = min(p_lo + PPG, has_input ? 8 : 6);
+        if (p_lo >= p_hi) return;                           // the du/dv group of a pass that starts from zero
+        uint32_t bytes = (uint32_t)(sizeof(T) * RH * kSorRegionW) * (uint32_t)(p_hi - p_lo);
+        if (p_lo == 0) bytes += (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW - RH * kSorRegionW));
+        mbar_expect_tx(&full_bar[g], bytes);
+        for (int p = p_lo; p < p_hi; p++) {
+            if (p == 0) tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar[g]);
+            else tma_load_2d(&st.pl[p - 1][0][0], (&maps.dxy) + (p - 1), rx0, ry0, &full_bar[g]);
         }
+    };
+    auto issue = [&](int tile) {
+        for (int g = 0; g < NG; g++) issue_group(tile, g);
     };
 
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        for (int g = 0; g < NG; g++) mbar_init(&full_bar[g], 1);
         mbar_fence_init();
     }
     // row-band split: the neighbours' previous pass must be complete (its halo rows are in our input planes, and
@@ -433,34 +445,31 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         const int rx0 = tx * step_x, ry0 = ty * step_y;   // even by construction
         const int xa = rx0 + 2 * lane, ya = ry0 + wp * R;
 
-        if (!(PF_SORX & 4)) mbar_wait(&full_bar, parity);
-        parity ^= 1;
-
         T w[R][2], dxy[R][2], iu[R][2], iv[R][2], bu[R][2], bv[R][2], du[R][2], dv[R][2];
         T wl[R], wr[R], wu[2];   // wl / wr: weights towards the neighbouring lanes' columns, zero at the region edge
+        // stage -> registers, one plane (compile-time index after unrolling)
+        auto unpack = [&](const int p) {
+            if (p == 0) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = wp * R + r;
-            V2 t = *reinterpret_cast<const V2*>(&st.phi[row + 1][2 * lane + 4]);
-            w[r][0] = t.x * alpha; w[r][1] = t.y * alpha;
-            wl[r] = lane == 0 ? (T)0 : st.phi[row + 1][2 * lane + 3] * alpha;
-            wr[r] = lane == 31 ? (T)0 : w[r][1];
-            t = *reinterpret_cast<const V2*>(&st.pl[0][row][2 * lane]); dxy[r][0] = t.x; dxy[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[1][row][2 * lane]); iu[r][0] = t.x; iu[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[2][row][2 * lane]); iv[r][0] = t.x; iv[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[3][row][2 * lane]); bu[r][0] = t.x; bu[r][1] = t.y;
-            t = *reinterpret_cast<const V2*>(&st.pl[4][row][2 * lane]); bv[r][0] = t.x; bv[r][1] = t.y;
-            if (has_input) {
-                t = *reinterpret_cast<const V2*>(&st.pl[5][row][2 * lane]); du[r][0] = t.x; du[r][1] = t.y;
-                t = *reinterpret_cast<const V2*>(&st.pl[6][row][2 * lane]); dv[r][0] = t.x; dv[r][1] = t.y;
-            } else {
-                du[r][0] = du[r][1] = dv[r][0] = dv[r][1] = 0;
+                for (int r = 0; r < R; r++) {
+                    const int row = wp * R + r;
+                    V2 t = *reinterpret_cast<const V2*>(&st.phi[row + 1][2 * lane + 4]);
+                    w[r][0] = t.x * alpha; w[r][1] = t.y * alpha;
+                    wl[r] = lane == 0 ? (T)0 : st.phi[row + 1][2 * lane + 3] * alpha;
+                    wr[r] = lane == 31 ? (T)0 : w[r][1];
+                }
+                V2 t = *reinterpret_cast<const V2*>(&st.phi[wp * R][2 * lane + 4]);
+                wu[0] = t.x * alpha; wu[1] = t.y * alpha;
+                return;
             }
-        }
-        {
-            V2 t = *reinterpret_cast<const V2*>(&st.phi[wp * R][2 * lane + 4]);
-            wu[0] = t.x * alpha; wu[1] = t.y * alpha;
-        }
+            T (*dst)[2] = p == 1 ? dxy : p == 2 ? iu : p == 3 ? iv : p == 4 ? bu : p == 5 ? bv : p == 6 ? du : dv;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (p >= 6 && !has_input) { dst[r][0] = dst[r][1] = 0; continue; }
+                V2 t = *reinterpret_cast<const V2*>(&st.pl[p - 1][wp * R + r][2 * lane]);
+                dst[r][0] = t.x; dst[r][1] = t.y;
+            }
+        };
         auto publish = [&](int b) {
             *reinterpret_cast<V2*>(&ex[b][0][wp][0][2 * lane]) = V2{du[0][0], du[0][1]};
             *reinterpret_cast<V2*>(&ex[b][1][wp][0][2 * lane]) = V2{dv[0][0], dv[0][1]};
@@ -468,12 +477,18 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
             *reinterpret_cast<V2*>(&ex[b][1][wp][1][2 * lane]) = V2{dv[R - 1][0], dv[R - 1][1]};
         };
         int buf = 0;
-        publish(0);
-        __syncthreads();   // stage consumed by everyone, exchange rows published
-        {
-            const int next = tile + gridDim.x;
-            if (tid == 0 && next < ntiles) issue(next);   // overlaps the sweeps below
+        const int next = tile + gridDim.x;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const bool in_flight = has_input || g * PPG < 6;
+            if (in_flight && !(PF_SORX & 4)) mbar_wait(&full_bar[g], parity);
+#pragma unroll
+            for (int p = g * PPG; p < (g + 1) * PPG; p++) unpack(p);
+            if (g == NG - 1) publish(0);
+            __syncthreads();   // group consumed by everyone (last group: exchange rows published)
+            if (tid == 0 && next < ntiles) issue_group(next, g);   // overlaps the rest of the unpacking and the sweeps below
         }
+        parity ^= 1;
 
         // one pixel of row r (compile-time after unrolling), column p = (r + c) & 1
         auto update = [&](const int r, const int c, T up_du, T up_dv, T dn_du, T dn_dv) {

@@ -31,6 +31,9 @@
 // Critical path: W + 31 + NS steps of march + ~(32 + hand-off) per band + ~(NS + hand-off) per sweep group, against
 // the (W + H + 2 nsor) grid-wide barriers of k_sor_wavefront.
 #pragma once
+#ifndef PF_LEX_F32_FOLD
+#define PF_LEX_F32_FOLD 0
+#endif
 #include <type_traits>
 #include "common.cuh"
 #include "sor.cuh"
@@ -223,10 +226,13 @@ __global__ void __launch_bounds__((NS + 3) * 32, 1) k_sor_lex(LexArgs<T> a) {
         }
         // the update of one pixel, in the reference's operation order (missing neighbours contribute +0)
         auto update = [&](T cw, T wl, T wu, V2 r, V2 u, V2 d, T& nu, T& nv) {
-            if constexpr (sizeof(T) == 4) {
-                // FP32 (no reference bits to match): everything that does not need this step's ring reads is folded
-                // beforehand, leaving four dependent operations for du and one more for dv (each dependent FMA costs ~8
-                // cycles with two lock-stepped warps per scheduler)
+            if constexpr (sizeof(T) == 4 && PF_LEX_F32_FOLD) {
+                // FP32 experiment (-DPF_LEX_F32_FOLD=1; off): everything that does not need this step's ring reads is
+                // folded beforehand, leaving four dependent operations for du and one more for dv (each dependent FMA
+                // costs ~8 cycles with two lock-stepped warps per scheduler): 393 instead of 415 cycles per step.  Not the
+                // default because the coarse levels of config 5 sit next to a bifurcation: with this association 5 of
+                // 8.3 M pixels end 1.2 px from the reference (tools/hybrid_repro.py), with the reference's own operation
+                // order -- the code below, FP32 rounding being the only difference -- every pixel stays within 0.2 px.
                 const T au = one_m * oc_du + n_b.x * (n_c.x - n_a.y * oc_dv);   // no ring value in here
                 const T av = one_m * oc_dv + n_b.y * n_c.y;
                 const T ku = n_b.x * a.alpha, kv = n_b.y * a.alpha;

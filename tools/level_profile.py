@@ -1,5 +1,5 @@
 """Per-level, per-phase CUDA-event times of one eager solve (developer tool).
-usage: python tools/level_profile.py [width] [mode]"""
+usage: python tools/level_profile.py [width] [mode] [tuning]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,8 +9,9 @@ from conftest import load_frame
 
 w = int(sys.argv[1]) if len(sys.argv) > 1 else 1920
 mode = sys.argv[2] if len(sys.argv) > 2 else "fp32_redblack"
+tuning = sys.argv[3] if len(sys.argv) > 3 else "throughput"
 a, b = load_frame(w, 1), load_frame(w, 2)
-plan = pyflow.FlowPlan(a.shape[0], a.shape[1], 3, mode=mode)
+plan = pyflow.FlowPlan(a.shape[0], a.shape[1], 3, mode=mode, tuning=tuning)
 plan.upload(a, b)
 plan.solve(2)
 ms = plan.solve(5) / 5
