@@ -176,7 +176,10 @@ int pf_device_count(void) {
 
 void* pf_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    // PF_HOST_ALLOC_WC=1 (experiment): write-combined pages -- not snooped during DMA, very slow to READ from the CPU, so
+    // only for buffers the host fills and the GPU reads
+    static const bool wc = [] { const char* e = getenv("PF_HOST_ALLOC_WC"); return e && atoi(e) != 0; }();
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0)) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }

@@ -49,6 +49,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     constexpr int BROWS = (SH + SEG - 1) / SEG;      // blend rows per thread
     constexpr int UW = TX + 2, UH = TY + 2, PW = TX + 1, PH = TY + 1;
     static_assert(TY % SEG == 0, "tile height must split into SEG segments");
+    static_assert(4 * (TY + 4) <= 64 * SEG, "one thread per entry of the four halo columns of the blend tile");
     static_assert(2 * UW * UH <= RHt * HW + SH * BW, "u/v tiles alias hs + bl");
 
     // the alignment is declared on the dynamic segment itself (TMA destinations need 128 B); going
@@ -176,7 +177,20 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
             }
         };
         vstage(col, seg);
-        if (tid < 4 * SEG) vstage(TX + (tid & 3), tid >> 2);
+        // the four halo columns right of the tile: one output per thread (the first 4 * SH threads, spread over several
+        // warps) instead of a second sliding pass by half a warp, which every other warp of the CTA waited for
+        if (tid < 4 * SH) {
+            const int bx = TX + (tid & 3), by = tid >> 2;
+            const T* hcol = &sm.hs[0][0] + bx;
+            T acc = 0;
+            acc += hcol[(by + 0) * HW] * g0; acc += hcol[(by + 1) * HW] * g1; acc += hcol[(by + 2) * HW] * g2;
+            acc += hcol[(by + 3) * HW] * g3; acc += hcol[(by + 4) * HW] * g4;
+            const T s1v = s1t[by * RW + bx + 2];
+            const T t = s1v * (T)0.4;
+            sm.bl[by][bx] = t + acc * (T)0.6;
+            const int ccx = bx - 2, ccy = by - 2;
+            if (ccx < TX && ccy >= 0 && ccy < TY) sm.dt[ccy][ccx] = acc - s1v;
+        }
         __syncthreads();
         // both input stages of this channel are free: prefetch channel c+2 into them
         if (tid == 0) {

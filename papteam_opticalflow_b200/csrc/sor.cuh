@@ -345,6 +345,11 @@ struct SorStage {
 #ifndef PF_SOR_GROUPS
 #define PF_SOR_GROUPS 1
 #endif
+// developer build (tools/build_variant.sh stats -DPF_SOR_STATS=1): CTAs 0 and 100 print where the cycles of their tile
+// visits went (waiting for the stage, stage -> registers, sweeps, write-back)
+#ifndef PF_SOR_STATS
+#define PF_SOR_STATS 0
+#endif
 // developer ablation builds (tools/sor_ablation.sh): bit 0 = no sweeps, bit 1 = no write-back, bit 2 = no TMA loads
 #ifndef PF_SORX
 #define PF_SORX 0
@@ -381,19 +386,26 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
     const int ntiles = ntx * nty;
     const T one_m = (T)1 - omega;
 
-    // plane p (0 phi, 1 dxy, 2 iu, 3 iv, 4 bu, 5 bv, 6 du, 7 dv) travels in group p / PPG
+    // plane p (0 phi, 1 dxy, 2 iu, 3 iv, 4 bu, 5 bv, 6 du, 7 dv) travels in group p / PPG.  The copies of a group are
+    // issued by DIFFERENT warps (lane 0 of warp p issues plane p) and the byte count is armed by thread 0: issued by one
+    // thread, the eight UTMALDG (each a uniform-datapath sequence of ~60 cycles) kept warp 0, and with it the first
+    // half-sweep barrier of the whole CTA, ~500 cycles behind on every tile (tools/sor_stats.py).  A copy may complete
+    // before the count is armed: the transaction count goes negative and the phase cannot complete without the arrival.
+    static_assert(NW >= 8, "one issuing warp per plane");
     auto issue_group = [&](int tile, int g) {
         if (PF_SORX & 4) return;
-        const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
-        const int rx0 = tx * step_x, ry0 = ty * step_y;
         const int p_lo = g * PPG, p_hi = min(p_lo + PPG, has_input ? 8 : 6);
         if (p_lo >= p_hi) return;                           // the du/dv group of a pass that starts from zero
-        uint32_t bytes = (uint32_t)(sizeof(T) * RH * kSorRegionW) * (uint32_t)(p_hi - p_lo);
-        if (p_lo == 0) bytes += (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW - RH * kSorRegionW));
-        mbar_expect_tx(&full_bar[g], bytes);
-        for (int p = p_lo; p < p_hi; p++) {
-            if (p == 0) tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar[g]);
-            else tma_load_2d(&st.pl[p - 1][0][0], (&maps.dxy) + (p - 1), rx0, ry0, &full_bar[g]);
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)(sizeof(T) * RH * kSorRegionW) * (uint32_t)(p_hi - p_lo);
+            if (p_lo == 0) bytes += (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW - RH * kSorRegionW));
+            mbar_expect_tx(&full_bar[g], bytes);
+        }
+        if (lane == 0 && wp >= p_lo && wp < p_hi) {
+            const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
+            const int rx0 = tx * step_x, ry0 = ty * step_y;
+            if (wp == 0) tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar[g]);
+            else tma_load_2d(&st.pl[wp - 1][0][0], (&maps.dxy) + (wp - 1), rx0, ry0, &full_bar[g]);
         }
     };
     auto issue = [&](int tile) {
@@ -436,9 +448,14 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         }
     }
     __syncthreads();
+    if (peer.wait_flag[0] || peer.wait_flag[1])      // every issuing thread orders the acquire above before its tile loads
+        asm volatile("fence.proxy.async.global;" ::: "memory");
     int tile = peer_lost ? ntiles : blockIdx.x;      // a lost neighbour: do nothing, still signal below
-    if (tid == 0 && tile < ntiles) issue(tile);
+    if (tile < ntiles) issue(tile);
     uint32_t parity = 0;
+    long long sc_wait = 0, sc_unpack = 0, sc_sweep = 0, sc_wb = 0, sc_t0 = 0, sc_first = 0;
+    int sc_n = 0;
+    if (PF_SOR_STATS) sc_t0 = clock64();
 
     for (; tile < ntiles; tile += gridDim.x) {
         const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
@@ -478,17 +495,21 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         };
         int buf = 0;
         const int next = tile + gridDim.x;
+        long long sc_a = 0, sc_b = 0;
+        if (PF_SOR_STATS) sc_a = clock64();
 #pragma unroll
         for (int g = 0; g < NG; g++) {
             const bool in_flight = has_input || g * PPG < 6;
             if (in_flight && !(PF_SORX & 4)) mbar_wait(&full_bar[g], parity);
+            if (PF_SOR_STATS && g == 0) { sc_b = clock64(); sc_wait += sc_b - sc_a; if (!sc_n) sc_first = sc_b - sc_a; }
 #pragma unroll
             for (int p = g * PPG; p < (g + 1) * PPG; p++) unpack(p);
             if (g == NG - 1) publish(0);
             __syncthreads();   // group consumed by everyone (last group: exchange rows published)
-            if (tid == 0 && next < ntiles) issue_group(next, g);   // overlaps the rest of the unpacking and the sweeps below
+            if (next < ntiles) issue_group(next, g);   // overlaps the rest of the unpacking and the sweeps below
         }
         parity ^= 1;
+        if (PF_SOR_STATS) { sc_a = clock64(); sc_unpack += sc_a - sc_b; }
 
         // one pixel of row r (compile-time after unrolling), column p = (r + c) & 1
         auto update = [&](const int r, const int c, T up_du, T up_dv, T dn_du, T dn_dv) {
@@ -545,6 +566,7 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
             }
         }
 
+        if (PF_SOR_STATS) { sc_b = clock64(); sc_sweep += sc_b - sc_a; }
         const int ox_lo = tx > 0 ? rx0 + HL : 0;
         const int ox_hi = (rx0 + kSorRegionW >= W) ? W : rx0 + kSorRegionW - HL;
         const int oy_lo = ty > 0 ? ry0 + HL : 0;
@@ -613,7 +635,11 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
                 }
             }
         }
+        if (PF_SOR_STATS) { sc_wb += clock64() - sc_b; sc_n++; }
     }
+    if (PF_SOR_STATS && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100) && sc_n > 0)
+        printf("SORSTAT cta %d %dx%d nsw %d tiles %d | total %lld cycles: wait %lld (first %lld) unpack %lld sweeps %lld write-back+rest %lld\n", blockIdx.x,
+               W, H, nsw, sc_n, clock64() - sc_t0, sc_wait, sc_first, sc_unpack, sc_sweep, sc_wb);
     // row-band split: this CTA is done reading and writing -- tell the neighbours (one arrival per CTA)
     if (peer.signal_flag[0] || peer.signal_flag[1]) {
         __syncthreads();
