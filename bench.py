@@ -203,6 +203,37 @@ def barrier(dist):
         torch.cuda.synchronize()
 
 
+def node_dma_ceiling(dist, local, n_gpus):
+    """What the NODE can move between pinned host memory and its GPUs when every rank copies at once, in both directions,
+    with nothing but cudaMemcpyAsync (torch pinned tensors; the library is not involved): the ceiling of the float64
+    end-to-end leg at N > 1 (182 MB of DMA per pair).  Measured 8 x B200, KVM guest, one visible NUMA node: 187 GB/s
+    host->device alone, 95 GB/s device->host alone, 128 GB/s with both directions busy (tools/pcie_ceiling.py)."""
+    import torch
+    nb, reps = 48 << 20, 12
+    failed = 0.0
+    try:
+        hs = [torch.empty(nb, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+        ds = [torch.empty(nb, dtype=torch.uint8, device="cuda:%d" % local) for _ in range(4)]
+        s_in, s_out = torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)
+    except Exception:
+        failed = 1.0
+    if dist_max(dist, local, failed) > 0:      # every rank takes the same branch: the loops below hold barriers
+        return None
+    def run(k):
+        barrier(dist)
+        t0 = time.perf_counter()
+        for i in range(k):
+            with torch.cuda.stream(s_in):
+                ds[i % 2].copy_(hs[i % 2], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hs[2 + i % 2].copy_(ds[2 + i % 2], non_blocking=True)
+        torch.cuda.synchronize()
+        return dist_max(dist, local, time.perf_counter() - t0)
+    run(2)
+    dt = run(reps)
+    return n_gpus * reps * 2 * nb / dt / 1e9
+
+
 def run_reference(args):
     """The reference arm: the reference's own OpenMP implementation of the path on the box's host cores, one FULL
     1920x1080 pair of the same workload per step (no extrapolation).  Rank 0 alone works."""
@@ -464,7 +495,12 @@ def run_ours(args):
 
     # ---- BASELINE configs[4] at N > 1: rank 0 splits ONE 4K pair into row bands over all N GPUs while the others wait ----
     rowband = None
+    dma_ceiling = None
     if dist is not None:
+        try:
+            dma_ceiling = node_dma_ceiling(dist, local, args.gpus)
+        except Exception:
+            dma_ceiling = None
         barrier(dist)
         if not args.no_rowband:
             # The other ranks must leave their GPUs idle while rank 0 drives all of them: a NCCL barrier would park a
@@ -566,6 +602,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(B * d2h_pair), "ms_per_step": 1000 * e2e_s / args.steps,
                     "legs_ms_per_pair_rank0": leg(legs),
                     "host_GBps": args.gpus * args.steps * B * (h2d_pair + d2h_pair) / e2e_s / 1e9,
+                    "node_dma_ceiling_GBps": dma_ceiling,
+                    "node_dma_ceiling_what": "all ranks copying pinned buffers in both directions at once with bare cudaMemcpyAsync "
+                                             "(no library code); N > 1 only -- the float64 leg cannot move more than this",
                     "api": "pyflow.coarse2fine_flow_batch -> pf_batch_flow (host float64 HWC in, host float64 vx, vy, warpI2 out)"},
             "e2e_flow_only": {"value": e2e_flow, "unit": "pairs/s", "h2d_bytes_per_step": int(B * h2d_pair),
                               "d2h_bytes_per_step": int(B * 2 * H * W * 8), "legs_ms_per_pair_rank0": leg(legs_flow),

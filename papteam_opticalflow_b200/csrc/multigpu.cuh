@@ -61,13 +61,20 @@ class MultiPlan {
         }
         PF_CUDA(cudaSetDevice(devs_[0]));
         PF_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-        // device-side flags need one GPU per band and peer access between neighbouring bands
+        // device-side flags need one GPU per band and peer access between neighbouring bands.  PF_MULTI_FLAGS_SHARED=1
+        // (tests on a single GPU) also allows them between bands that share a device, for the split solves whose passes
+        // leave room for the spinning CTAs of a waiting pass next to the CTAs of the pass they wait for (checked per solve)
         e = getenv("PF_MULTI_FLAGS");
         flags_ok_ = push_ && !(e && !atoi(e)) && ndev > 1;
+        const char* es = getenv("PF_MULTI_FLAGS_SHARED");
+        const bool allow_shared = es && atoi(es) != 0;
         for (int g = 0; g < ndev && flags_ok_; g++) {
             for (int h = 0; h < g; h++)
-                if (devs_[h] == devs_[g]) flags_ok_ = false;
-            if (g + 1 < ndev && flags_ok_) {
+                if (devs_[h] == devs_[g]) {
+                    if (allow_shared) flags_shared_ = true;
+                    else flags_ok_ = false;
+                }
+            if (g + 1 < ndev && flags_ok_ && devs_[g] != devs_[g + 1]) {
                 int a = 0, b = 0;
                 PF_CUDA(cudaDeviceCanAccessPeer(&a, devs_[g], devs_[g + 1]));
                 PF_CUDA(cudaDeviceCanAccessPeer(&b, devs_[g + 1], devs_[g]));
@@ -288,6 +295,19 @@ class MultiPlan {
         // device-side flags between the passes of this solve: possible when every row a band needs from another band
         // comes from an ADJACENT one (then the producing kernel pushes exactly those rows) and counters are left
         bool use_flags = flags_ok_ && sched.size() > 1 && flag_slot_ + (int)sched.size() <= kFlagSlots;
+        if (use_flags && flags_shared_) {
+            // bands on one device: at most one pass per band is resident at a time (a band's passes are ordered by its
+            // stream), so a waiting pass cannot starve the pass it waits for as long as one pass of EVERY band fits the SMs
+            for (size_t p = 0; p < sched.size() && use_flags; p++) {
+                int ctas = 0;
+                for (int g = 0; g < G; g++) {
+                    int tb, te;
+                    band(sched[p], g, tb, te);
+                    ctas += v[g].runner->grid_for(sched[p], te - tb);
+                }
+                if (ctas > v[0].runner->sms * v[0].runner->ctas_per_sm) use_flags = false;
+            }
+        }
         for (size_t p = 0; p + 1 < sched.size() && use_flags; p++)
             for (int g = 0; g < G && use_flags; g++) {
                 int tb, te;
@@ -405,6 +425,7 @@ class MultiPlan {
     bool graph_failed_ = false;
     bool push_ = true;     // halo rows stored by the producing kernel into the neighbour (PF_MULTI_PULL=1: copy-engine pulls)
     bool flags_ok_ = false;                 // one GPU per band with peer access: passes ordered by device-side counters
+    bool flags_shared_ = false;             // PF_MULTI_FLAGS_SHARED=1 and some bands share a device
     std::vector<unsigned int*> flags_;      // per device: kFlagSlots x {from above, from below}
     int flag_slot_ = 0, flag_solves_ = 0;
 };

@@ -373,6 +373,24 @@ def test_row_band_split_equals_single_gpu(nbands):
     assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
 
 
+def test_row_band_split_flag_ordering_on_one_gpu(monkeypatch):
+    """The ordering a real multi-GPU split uses -- device-side counters: every CTA of a pass bumps a counter in its
+    neighbours' memory, the CTAs of their next pass spin on it before their first tile load; one multi-'device' CUDA
+    graph -- exercised on ONE GPU (PF_MULTI_FLAGS_SHARED=1: the bands share the device; allowed for the solves whose
+    passes leave room for a spinning pass next to the pass it waits for).  Same bits as the single-GPU solve."""
+    monkeypatch.setenv("PF_MULTI_FLAGS_SHARED", "1")
+    a, b = load_frame(480, 1), load_frame(480, 2)
+    u0, v0, w0 = pyflow.coarse2fine_flow(a, b, 0.012, 0.75, 20, 7, 1, 30, 0, mode="fp32_redblack")
+    for nbands in (2, 3):
+        # (a split threshold no other test uses: cached multi-GPU plans are keyed by it, and the switch is read at creation)
+        u, v, w2, st = pyflow.coarse2fine_flow_multigpu(a, b, devices=[0] * nbands, split_min_pixels=20001 + nbands)
+        assert st["split_solves"] > 0 and st["flag_solves"] > 0 and st["graph"], st
+        assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+        u, v, w2, st2 = pyflow.coarse2fine_flow_multigpu(a, b, devices=[0] * nbands, split_min_pixels=20001 + nbands)   # graph replay
+        assert st2["flag_solves"] == st["flag_solves"]
+        assert np.array_equal(u, u0) and np.array_equal(v, v0) and np.array_equal(w2, w0)
+
+
 def test_row_band_split_on_real_peers_if_present():
     from papteam_opticalflow_b200 import _lib
     n = _lib.lib().pf_device_count()
