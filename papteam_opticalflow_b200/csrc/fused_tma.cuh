@@ -61,7 +61,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     __shared__ T sm_phi[PW * PH];
 
     const int W = a.w, H = a.h;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int x0 = blockIdx.x * TX, y0 = (blockIdx.y + a.ty0) * TY;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = tid & (TX - 1), seg = tid / TX;
     const int C = a.wf.c;

@@ -464,7 +464,9 @@ inline dim3 warp_grid(int w, int h) {
 template <typename T>
 __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img<T> warp, T* __restrict__ u,
                               T* __restrict__ v, const T* __restrict__ du,
-                              const T* __restrict__ dv, int fpitch) {
+                              const T* __restrict__ dv, int fpitch, int warp_lo = 0, int warp_hi = 0x7fffffff) {
+    // rows outside [warp_lo, warp_hi) only get their flow update (row-band split over several GPUs: a device warps the
+    // rows its own band's assembly reads; the flow itself stays complete everywhere, it accumulates across iterations)
     // the four warps of a CTA take the same columns of four consecutive rows: their bilinear taps
     // share image rows (row y+1 of one warp is row y of the next), which L1 then serves
     const int W = im1.w, H = im1.h;
@@ -504,6 +506,7 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
             u[of] = uu[i];
             v[of] = vv[i];
         }
+        if (y < warp_lo || y >= warp_hi) continue;   // (warp-uniform: a warp works on one row)
         T fx, fy;
         const SamplePos px = sample_pos(x, uu[i], W, fx), py = sample_pos(y, vv[i], H, fy);
         if (px.out || py.out) continue;
@@ -514,6 +517,7 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
         o00[i] = y0 * im2.pitch + x0; o01[i] = y1 * im2.pitch + x0;
         o10[i] = y0 * im2.pitch + x1; o11[i] = y1 * im2.pitch + x1;
     }
+    if (y < warp_lo || y >= warp_hi) return;
     const int orow1 = y * im1.pitch, orow_w = y * warp.pitch;
     // the gathers of channel k+1 are issued before channel k is reduced and stored (two register
     // buffers), so a thread has up to 8*kWarpPix loads in flight and the memory round trips of
@@ -963,6 +967,7 @@ struct FusedArgs {
     int w, h, pitch;               // pitch of the scalar planes
     T alpha, omega, eps;
     Taps<T> g5, d5;
+    int ty0 = 0;                   // first tile row of this launch (k_fused_tma; a row band of the level, multigpu.cuh)
 };
 
 // psi = 1 / (2 sqrt(t + eps)).  FP64 keeps the reference's expression; FP32 uses the hardware

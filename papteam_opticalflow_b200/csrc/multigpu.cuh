@@ -231,10 +231,26 @@ class MultiPlan {
             for (int it = 0; it < plans_[0]->n_outer_at(k); it++) {
                 for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_getdxs(k); }
                 for (int hh = 0; hh < P.n_inner; hh++) {
-                    for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_assemble(k, hh); }
+                    for (int g = 0; g < G; g++) {
+                        on(g);
+                        int lo = 0, hi = -1;
+                        sor_rows(k, g, lo, hi);          // split solve: only the rows this device's band reads
+                        plans_[g]->ph_assemble(k, hh, lo, hi);
+                    }
                     sor(k);
                 }
-                for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_update(k); }
+                const bool last_it = it + 1 == plans_[0]->n_outer_at(k);
+                for (int g = 0; g < G; g++) {
+                    on(g);
+                    int lo = 0, hi = -1;
+                    if (!last_it) sor_rows(k, g, lo, hi);     // (after the last iteration nobody reads the warped features again:
+                    if (hi < 0) plans_[g]->ph_update(k);      //  the next level warps from scratch; kept whole for simplicity)
+                    else {
+                        // the assembly of rows [lo, hi) works on whole tile rows and reads the warped features 4 rows beyond them
+                        const int ty = plans_[g]->fused_tile_rows(k);
+                        plans_[g]->ph_update(k, lo / ty * ty - 4, (hi + ty - 1) / ty * ty + 4);
+                    }
+                }
             }
         }
         for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_end(); }
@@ -258,6 +274,37 @@ class MultiPlan {
         counter += (long long)bytes;
     }
 
+    // will the SOR solve of level k be split into row bands?  (the one rule sor() and sor_rows() share)
+    bool sor_is_split(int k, const std::vector<SorRunner<float>::SorPass>& sched, const SorRunner<float>& r) const {
+        const int G = (int)devs_.size();
+        const int w = plans_[0]->level_w(k), h = plans_[0]->level_h(k), nsor = plans_[0]->n_sor_at(k);
+        bool split = G > 1 && (long long)w * h >= split_min_ && r.use_tma && !r.simple_rb && nsor > 0;
+        for (auto& ps : sched)
+            if (ps.ty.ntiles < G) split = false;          // every device needs at least one tile row
+        return split;
+    }
+    // Rows of the coefficient planes device g's band reads in ANY pass of the split solve of level k (the union of its
+    // tile rows' regions, plus the phi row above): the only rows its assembly has to produce.  The whole level when the
+    // solve is not split (lo = 0, hi = -1).  PF_MULTI_ASM_SPLIT=0 keeps the redundant whole-level assembly.
+    void sor_rows(int k, int g, int& lo, int& hi) {
+        typedef SorRunner<float> Runner;
+        lo = 0; hi = -1;
+        static const bool on_ = [] { const char* e = getenv("PF_MULTI_ASM_SPLIT"); return !(e && !atoi(e)); }();
+        if (!on_) return;
+        const int G = (int)devs_.size();
+        const int w = plans_[0]->level_w(k), h = plans_[0]->level_h(k), nsor = plans_[0]->n_sor_at(k);
+        Plan<float>::SorView v = plans_[g]->sor_view();
+        std::vector<Runner::SorPass> sched = v.runner->schedule(w, h, nsor);
+        if (!sor_is_split(k, sched, *v.runner)) return;
+        int a = h, b = 0;
+        for (auto& ps : sched) {
+            const int tb = (int)((long long)g * ps.ty.ntiles / G), te = (int)((long long)(g + 1) * ps.ty.ntiles / G);
+            a = std::min(a, ps.in_lo(tb));
+            b = std::max(b, ps.in_hi(te - 1, h));
+        }
+        lo = a; hi = b;
+    }
+
     void sor(int k) {
         typedef SorRunner<float> Runner;
         const int G = (int)devs_.size();
@@ -265,9 +312,7 @@ class MultiPlan {
         std::vector<Plan<float>::SorView> v;
         for (int g = 0; g < G; g++) v.push_back(plans_[g]->sor_view());
         std::vector<Runner::SorPass> sched = v[0].runner->schedule(w, h, nsor);
-        bool split = G > 1 && (long long)w * h >= split_min_ && v[0].runner->use_tma && !v[0].runner->simple_rb && nsor > 0;
-        for (auto& ps : sched)
-            if (ps.ty.ntiles < G) split = false;          // every device needs at least one tile row
+        const bool split = sor_is_split(k, sched, *v[0].runner);
         if (!split) {
             for (int g = 0; g < G; g++) { on(g); plans_[g]->ph_sor(k); }
             return;

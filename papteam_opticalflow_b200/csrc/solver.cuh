@@ -791,6 +791,7 @@ class Plan : public PlanBase {
     int n_outer_at(int k) const { return P.n_outer + k; }
     int n_sor_at(int k) const { return P.n_sor + 3 * k; }
     int level_w(int k) const { return geo_[k].w; }
+    int fused_tile_rows(int k) const { return small_tiles(geo_[k].w, geo_[k].h) ? kFTYs : kFTY; }   // tile height of k_fused_tma at level k
     int level_h(int k) const { return geo_[k].h; }
 
     // filter taps, eps, pointer roles on entry
@@ -928,9 +929,13 @@ class Plan : public PlanBase {
     }
 
     // -- Phases 1-4 of inner iteration hh: the linear system of S/OpticalFlow.cpp:295-448 --
-    void ph_assemble(int k, int hh) {
+    // rows [row_lo, row_hi) only (row-band split, multigpu.cuh: the rows this device's SOR band reads); the fused TMA
+    // kernel computes whole tile rows, the other paths always the whole level
+    void ph_assemble(int k, int hh, int row_lo = 0, int row_hi = -1) {
         Ctx& c = cx_;
         const int w = c.w, h = c.h, pitch = c.pitch;
+        if (row_hi < 0 || row_hi > h) row_hi = h;
+        row_lo = std::max(0, std::min(row_lo, row_hi));
         const T* cdu = hh > 0 ? du_ : nullptr;
         const T* cdv = hh > 0 ? dv_ : nullptr;
         if (fused_) {
@@ -946,10 +951,12 @@ class Plan : public PlanBase {
             if (fused_tma_) {
                 if (small_tiles(w, h)) {
                     size_t smem = sizeof(FusedSmem<T, kFTYs>) + 128;
-                    k_fused_tma<T, kFTYs, kFSEGs><<<dim3(ceil_div(w, 64), ceil_div(h, kFTYs)), 64 * kFSEGs, smem, st_>>>(c.fmaps, fa);
+                    fa.ty0 = row_lo / kFTYs;
+                    k_fused_tma<T, kFTYs, kFSEGs><<<dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), 64 * kFSEGs, smem, st_>>>(c.fmaps, fa);
                 } else {
                     size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
-                    k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(h, kFTY)), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
+                    fa.ty0 = row_lo / kFTY;
+                    k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(row_hi, kFTY) - fa.ty0), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
                 }
             } else {
                 k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
@@ -991,15 +998,18 @@ class Plan : public PlanBase {
     }
 
     // -- Phase6: update + warp (+ noise estimate in the parity mode) --
-    void ph_update(int k) {
+    // warp_lo / warp_hi: rows whose warped features this device will read again (row-band split, multigpu.cuh); the
+    // flow update always covers the whole level
+    void ph_update(int k, int warp_lo = 0, int warp_hi = 0x7fffffff) {
         Ctx& c = cx_;
         set_phase(PF_T_PHASE6_UPDATE, k);
+        if (bicubic_ || gmix_ || (kF64 && lex_)) { warp_lo = 0; warp_hi = 0x7fffffff; }   // these read the whole warped image
         if (bicubic_) {
             k_add_flow<T><<<grid2(c.w, c.h), 128, 0, st_>>>(u_, v_, du_, dv_, c.w, c.pitch);
             launches_++;
             bicubic_inner(k, 1);   // S/OpticalFlow.cpp:517-521: warpImageBicubicRef + threshold()
         } else {
-            k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch);
+            k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch, warp_lo, warp_hi);
             launches_++;
         }
         if (gmix_) {   // S/OpticalFlow.cpp:524-527
