@@ -7,6 +7,7 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <utility>
 
 #include "../../include/pyflow_b200.h"
 
@@ -116,6 +117,41 @@ inline void stream_wait_blocking(cudaStream_t st) {
     if (e == cudaSuccess) e = cudaEventSynchronize(ev);
     cudaEventDestroy(ev);
     PF_CUDA(e);
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// One pair alone is a chain of ~1 450 dependent kernels, most of them shorter than 20 us, and every kernel boundary costs
+// the drain of the previous grid plus the launch of the next one.  Kernels that start with pdl_trigger() / pdl_wait() and
+// are launched through launch_chain() with `pdl` set let the NEXT kernel of the stream be launched, scheduled onto the SMs
+// the previous grid has already left and run its prologue (barrier initialisation, index arithmetic) while the previous
+// grid is still finishing; pdl_wait() returns when the previous grid has completed and its memory is visible, so every
+// global access stays after it.  Launched the ordinary way the two instructions do nothing.  Only latency-tuned plans would
+// use it: with many pairs in flight a waiting grid would hold SMs that another pair's kernels could use.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// MEASURED AND OFF BY DEFAULT (PF_PDL=1 enables it): graph replay of a 1920x1080 pair 17.59 ms without, 17.92 ms with it;
+// 480x270: 6.32 / 6.43 ms (tools/pdl_check.py, identical results).  Inside a captured graph a kernel boundary already costs
+// well under a microsecond, and an early-launched grid only adds CTAs that wait on the SMs.
+inline bool pdl_allowed() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PF_PDL");
+        v = (e && atoi(e)) ? 1 : 0;
+    }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && pdl_allowed()) ? 1 : 0;
+    PF_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
 inline bool mode_is_fp64(int mode) { return mode == PF_MODE_FP64_WAVEFRONT || mode == PF_MODE_FP64_REDBLACK; }

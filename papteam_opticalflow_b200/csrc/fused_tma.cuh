@@ -86,6 +86,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         tma_load_2d(&sm.raw[su][0][0], &maps.u, x0 - 4, y0 - 1, &uv_bar);
         tma_load_2d(&sm.s1[su][0][0], &maps.v, x0 - 4, y0 - 1, &uv_bar);
     };
+    pdl_trigger();
     if (tid == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
@@ -93,6 +94,7 @@ k_fused_tma(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_wait();   // nothing above touches global memory
     if (tid == 0) {
         issue(0);
         if (C > 1) issue(1);

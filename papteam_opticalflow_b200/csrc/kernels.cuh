@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(128) k_update_warp(Img<T> im1, Img<T> im2, Img
     // rows its own band's assembly reads; the flow itself stays complete everywhere, it accumulates across iterations)
     // the four warps of a CTA take the same columns of four consecutive rows: their bilinear taps
     // share image rows (row y+1 of one warp is row y of the next), which L1 then serves
+    pdl_trigger();
+    pdl_wait();
     const int W = im1.w, H = im1.h;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 #if PF_WARP_ROWS

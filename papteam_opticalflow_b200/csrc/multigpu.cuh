@@ -53,6 +53,7 @@ class MultiPlan {
             Params q = p;
             q.device = devs_[g];
             plans_.emplace_back(new Plan<float>(q));
+            plans_.back()->set_pdl(false);      // flag-ordered passes and cross-device edges: ordinary launches only
             cudaEvent_t e1, e2;
             PF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
             PF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));

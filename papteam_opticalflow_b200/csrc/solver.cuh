@@ -137,6 +137,7 @@ struct SorRunner {
     bool lex = false, hybrid = false, simple_rb = false, use_tma = true, small_regions = false;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     int tune = PF_TUNE_THROUGHPUT;
+    bool pdl = false;    // launch the tile kernel with programmatic stream serialisation (common.cuh; latency-tuned plans)
     int lex_from = -1;   // experiment (PF_LEX_FROM=k): pyramid levels >= k use the lexicographic kernel in every mode
     bool lex_band = true;          // k_sor_lex (band-march) instead of the grid-synchronised k_sor_wavefront (PF_LEX_IMPL=coop)
     static constexpr int kLexNS = 8;
@@ -219,8 +220,8 @@ struct SorRunner {
         m.bv = make_plane_map(a.bv, a.w, a.h, a.pitch, kSorRegionW, RH);
         m.du = make_plane_map(du_out, a.w, a.h, a.pitch, kSorRegionW, RH);   // not read: the solve starts from zero
         m.dv = make_plane_map(dv_out, a.w, a.h, a.pitch, kSorRegionW, RH);
-        k_sor_rb_tma<T, R, NW><<<1, NW * 32, small_smem_bytes<R, NW>(), st>>>(m, du_out, dv_out, a.w, a.h, a.pitch, a.alpha, a.omega, nsor, 0, 1, 1,
-                                                                              kSorRegionW, RH, 0, SorPeer<T>());
+        launch_chain(pdl, k_sor_rb_tma<T, R, NW>, dim3(1), dim3(NW * 32), small_smem_bytes<R, NW>(), st, m, du_out, dv_out, a.w, a.h, a.pitch,
+                     a.alpha, a.omega, nsor, 0, 1, 1, kSorRegionW, RH, 0, SorPeer<T>());
     }
 
     // one launch of the tile kernel: sweeps fused, whether it reads du/dv, and its tiling
@@ -312,9 +313,9 @@ struct SorRunner {
             m.du = make_plane_map(ps.has_input ? du : du2, w, h, a.pitch, kSorRegionW, kRegionH);
             m.dv = make_plane_map(ps.has_input ? dv : dv2, w, h, a.pitch, kSorRegionW, kRegionH);
             size_t smem = sor_smem_bytes();
-            k_sor_rb_tma<T, kR, kNW><<<grid_for(ps, nrows), kNW * 32, smem, st>>>(
-                    m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
-                    ps.tx.step, ps.ty.step, ty_begin, peer);
+            launch_chain(pdl, k_sor_rb_tma<T, kR, kNW>, dim3(grid_for(ps, nrows)), dim3(kNW * 32), smem, st,
+                         m, du2, dv2, w, h, a.pitch, a.alpha, a.omega, ps.nsw, ps.has_input ? 1 : 0, ps.tx.ntiles, nrows,
+                         ps.tx.step, ps.ty.step, ty_begin, peer);
         } else {
             if (ty_begin != 0 || ty_end != ps.ty.ntiles) throw Error(PF_EUNSUPPORTED, "row-band split needs the TMA SOR kernel");
             k_sor_rb_tile<T, kR, kNW><<<dim3(ps.tx.ntiles, ps.ty.ntiles), kNW * 32, 0, st>>>(a, ps.nsw, ps.tx.step, ps.ty.step);
@@ -427,6 +428,7 @@ class Plan : public PlanBase {
             for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
             allocate();
             sor_.init(P.mode, P.device, st_, P.tune);
+            set_pdl(P.tune == PF_TUNE_LATENCY);
         } catch (...) {
             release();       // the destructor does not run for a half-built object (PF_ENOMEM is the realistic cause)
             throw;
@@ -788,6 +790,8 @@ class Plan : public PlanBase {
     Ctx cx_;
 
   public:
+    // programmatic dependent launch of the chain kernels (common.cuh): latency-tuned plans; never the plans of a MultiPlan
+    void set_pdl(bool on) { pdl_ = on; sor_.pdl = on; }
     int n_outer_at(int k) const { return P.n_outer + k; }
     int n_sor_at(int k) const { return P.n_sor + 3 * k; }
     int level_w(int k) const { return geo_[k].w; }
@@ -896,7 +900,7 @@ class Plan : public PlanBase {
             if (bicubic_) {
                 bicubic_inner(k, 0);   // S/OpticalFlow.cpp:814-815: no threshold() at the level start
             } else {
-                k_update_warp<T><<<warp_grid(w, h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, nullptr, nullptr, pitch);
+                launch_chain(pdl_, k_update_warp<T>, warp_grid(w, h), dim3(128), 0, st_, c.f1, c.f2, c.wf, u_, v_, (const T*)nullptr, (const T*)nullptr, pitch, 0, 0x7fffffff);
                 launches_++;
             }
         }
@@ -952,11 +956,11 @@ class Plan : public PlanBase {
                 if (small_tiles(w, h)) {
                     size_t smem = sizeof(FusedSmem<T, kFTYs>) + 128;
                     fa.ty0 = row_lo / kFTYs;
-                    k_fused_tma<T, kFTYs, kFSEGs><<<dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), 64 * kFSEGs, smem, st_>>>(c.fmaps, fa);
+                    launch_chain(pdl_, k_fused_tma<T, kFTYs, kFSEGs>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), dim3(64 * kFSEGs), smem, st_, c.fmaps, fa);
                 } else {
                     size_t smem = sizeof(FusedSmem<T, kFTY>) + 128;
                     fa.ty0 = row_lo / kFTY;
-                    k_fused_tma<T, kFTY, kFSEG><<<dim3(ceil_div(w, 64), ceil_div(row_hi, kFTY) - fa.ty0), 64 * kFSEG, smem, st_>>>(c.fmaps, fa);
+                    launch_chain(pdl_, k_fused_tma<T, kFTY, kFSEG>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTY) - fa.ty0), dim3(64 * kFSEG), smem, st_, c.fmaps, fa);
                 }
             } else {
                 k_fused_assemble<T, kFTX, kFTY, kFSEG><<<dim3(ceil_div(w, kFTX), ceil_div(h, kFTY)), kFTX * kFSEG, 0, st_>>>(fa);
@@ -1009,7 +1013,7 @@ class Plan : public PlanBase {
             launches_++;
             bicubic_inner(k, 1);   // S/OpticalFlow.cpp:517-521: warpImageBicubicRef + threshold()
         } else {
-            k_update_warp<T><<<warp_grid(c.w, c.h), 128, 0, st_>>>(c.f1, c.f2, c.wf, u_, v_, du_, dv_, c.pitch, warp_lo, warp_hi);
+            launch_chain(pdl_, k_update_warp<T>, warp_grid(c.w, c.h), dim3(128), 0, st_, c.f1, c.f2, c.wf, u_, v_, (const T*)du_, (const T*)dv_, c.pitch, warp_lo, warp_hi);
             launches_++;
         }
         if (gmix_) {   // S/OpticalFlow.cpp:524-527
@@ -1183,6 +1187,7 @@ class Plan : public PlanBase {
     }
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     bool bicubic_ = false, gmix_ = false;   // alternative solver branches
+    bool pdl_ = false;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;
     std::vector<Level> geo_;

@@ -412,10 +412,12 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
         for (int g = 0; g < NG; g++) issue_group(tile, g);
     };
 
+    pdl_trigger();
     if (tid == 0) {
         for (int g = 0; g < NG; g++) mbar_init(&full_bar[g], 1);
         mbar_fence_init();
     }
+    pdl_wait();   // everything above overlaps the tail of the previous kernel of the stream (launch_chain)
     // row-band split: the neighbours' previous pass must be complete (its halo rows are in our input planes, and
     // it no longer reads the planes this pass pushes into) before anything of this pass touches memory.  A neighbour
     // that is merely busy (another process on its GPU, time slicing, a debugger) is an ordinary scheduling delay:
