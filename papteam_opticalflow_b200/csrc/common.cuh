@@ -131,7 +131,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // MEASURED AND OFF BY DEFAULT (PF_PDL=1 enables it): graph replay of a 1920x1080 pair 17.59 ms without, 17.92 ms with it;
-// 480x270: 6.32 / 6.43 ms (tools/pdl_check.py, identical results).  Inside a captured graph a kernel boundary already costs
+// 480x270: 6.32 / 6.43 ms (tools/env_ab.py PF_PDL 0 1, identical results).  Inside a captured graph a kernel boundary already costs
 // well under a microsecond, and an early-launched grid only adds CTAs that wait on the SMs.
 inline bool pdl_allowed() {
     static int v = -1;

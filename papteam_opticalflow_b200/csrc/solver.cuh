@@ -16,6 +16,7 @@
 #include "sor.cuh"
 #include "sor_lex.cuh"
 #include "fused_tma.cuh"
+#include "fused_cp.cuh"
 #include "staging.hpp"
 
 namespace pf {
@@ -134,7 +135,7 @@ struct SorRunner {
     static constexpr int kR = kF64 ? 2 : PF_SOR_R;
     static constexpr int kNW = kF64 ? 16 : PF_SOR_NW;
     static constexpr int kRegionH = kR * kNW;
-    bool lex = false, hybrid = false, simple_rb = false, use_tma = true, small_regions = false;
+    bool lex = false, hybrid = false, simple_rb = false, use_tma = true, small_regions = false, small_four_warps = true;
     int forced_fuse = 0, coop_max_blocks = 1, sms = 148, ctas_per_sm = 1;
     int tune = PF_TUNE_THROUGHPUT;
     bool pdl = false;    // launch the tile kernel with programmatic stream serialisation (common.cuh; latency-tuned plans)
@@ -178,7 +179,11 @@ struct SorRunner {
             ctas_per_sm = std::max(1, per_sm);
             e = getenv("PF_SOR_SMALL");
             small_regions = !kF64 && !(e && !atoi(e));
-            if (small_regions) { init_small<2, 16>(); init_small<4, 16>(); }
+            if constexpr (!kF64) {
+                if (small_regions) { init_small<2, 16>(); init_small<4, 16>(); init_small<8, 4>(); init_small<10, 4>(); }
+                e = getenv("PF_SOR_SMALL_WARPS");      // 4 (default): the four-warp variants below; 16: round 2's R = 2 / 4, 16 warps
+                small_four_warps = !(e && atoi(e) == 16);
+            }
         }
         e = getenv("PF_LEX_IMPL");
         lex_band = !(e && !strcmp(e, "coop"));
@@ -372,7 +377,12 @@ struct SorRunner {
         }
         if (small_regions && use_tma && w <= kSorRegionW && h <= 64) {
             if constexpr (!kF64) {
-                if (h <= 32) launch_single_region<2, 16>(a, du2, dv2, nsor);
+                // four warps, one per scheduler, R = 8 / 10 rows each: a half-sweep is R independent updates issued back to
+                // back by ONE warp per scheduler plus a four-warp barrier, instead of sixteen warps each doing two updates
+                // between 512-thread barriers
+                if (small_four_warps && h <= 32) launch_single_region<8, 4>(a, du2, dv2, nsor);
+                else if (small_four_warps && h <= 40) launch_single_region<10, 4>(a, du2, dv2, nsor);
+                else if (h <= 32) launch_single_region<2, 16>(a, du2, dv2, nsor);
                 else launch_single_region<4, 16>(a, du2, dv2, nsor);
                 std::swap(du, du2);
                 std::swap(dv, dv2);
@@ -422,6 +432,14 @@ class Plan : public PlanBase {
                                          (int)(sizeof(FusedSmem<T, kFTY>) + 128)));
             PF_CUDA(cudaFuncSetAttribute(k_fused_tma<T, kFTYs, kFSEGs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(FusedSmem<T, kFTYs>) + 128)));
+            if constexpr (!kF64) {
+                // channel-parallel form for the coarse levels of latency-tuned plans (fused_cp.cuh): C groups of 64 * kCpSeg threads
+                e = getenv("PF_FUSED_CP");
+                fused_cp_ = !(e && !atoi(e)) && 64 * kCpSeg * fc_ <= 1024;
+                if (fused_cp_)
+                    PF_CUDA(cudaFuncSetAttribute(k_fused_cp<T, kFTYs, kCpSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)fused_cp_smem_bytes<T, kFTYs>(fc_)));
+            }
         }
         try {
             PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
@@ -953,7 +971,13 @@ class Plan : public PlanBase {
             fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = c.eps;
             fa.g5 = c.g5; fa.d5 = c.d5;
             if (fused_tma_) {
-                if (small_tiles(w, h)) {
+                if (small_tiles(w, h) && fused_cp_) {
+                    if constexpr (!kF64) {
+                        fa.ty0 = row_lo / kFTYs;
+                        launch_chain(pdl_, k_fused_cp<T, kFTYs, kCpSeg>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), dim3(64 * kCpSeg * fc_),
+                                     fused_cp_smem_bytes<T, kFTYs>(fc_), st_, c.fmaps, fa);
+                    }
+                } else if (small_tiles(w, h)) {
                     size_t smem = sizeof(FusedSmem<T, kFTYs>) + 128;
                     fa.ty0 = row_lo / kFTYs;
                     launch_chain(pdl_, k_fused_tma<T, kFTYs, kFSEGs>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), dim3(64 * kFSEGs), smem, st_, c.fmaps, fa);
@@ -1180,7 +1204,11 @@ class Plan : public PlanBase {
     // whatever the level (five channels through three stencil stages, one after the other), so the coarse levels are
     // bound by the latency of ONE tile; a 64x4 tile has half the rows to smooth (4+8 instead of 16+8) and a quarter of
     // the centre rows.  More halo work in total, which is why throughput-tuned plans keep 64x16.  Same arithmetic per pixel.
-    static constexpr int kFTYs = kF64 ? 8 : 4, kFSEGs = kF64 ? 8 : 4;
+#ifndef PF_FUSED_TYS
+#define PF_FUSED_TYS 4
+#define PF_FUSED_SEGS 4
+#endif
+    static constexpr int kFTYs = kF64 ? 8 : PF_FUSED_TYS, kFSEGs = kF64 ? 8 : PF_FUSED_SEGS;
     bool small_tiles(int w, int h) const {
         if (const char* e = getenv("PF_FUSED_SMALL")) return atoi(e) != 0 && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
         return P.tune == PF_TUNE_LATENCY && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
@@ -1188,6 +1216,8 @@ class Plan : public PlanBase {
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     bool bicubic_ = false, gmix_ = false;   // alternative solver branches
     bool pdl_ = false;
+    bool fused_cp_ = false;                  // channel-parallel assembly kernel on the small-tile levels (fused_cp.cuh)
+    static constexpr int kCpSeg = 2;
     int nlev_ = 0, fc_ = 0;
     SorRunner<T> sor_;
     std::vector<Level> geo_;

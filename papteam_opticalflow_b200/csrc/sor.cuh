@@ -391,7 +391,7 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
     // thread, the eight UTMALDG (each a uniform-datapath sequence of ~60 cycles) kept warp 0, and with it the first
     // half-sweep barrier of the whole CTA, ~500 cycles behind on every tile (tools/sor_stats.py).  A copy may complete
     // before the count is armed: the transaction count goes negative and the phase cannot complete without the arrival.
-    static_assert(NW >= 8, "one issuing warp per plane");
+    // (NW < 8, the small single-region variants: warp w issues planes w, w + NW, ...)
     auto issue_group = [&](int tile, int g) {
         if (PF_SORX & 4) return;
         const int p_lo = g * PPG, p_hi = min(p_lo + PPG, has_input ? 8 : 6);
@@ -401,11 +401,13 @@ const __grid_constant__ SorMaps maps, T* __restrict__ du_out, T* __restrict__ dv
             if (p_lo == 0) bytes += (uint32_t)(sizeof(T) * (Stage::PHH * Stage::PHW - RH * kSorRegionW));
             mbar_expect_tx(&full_bar[g], bytes);
         }
-        if (lane == 0 && wp >= p_lo && wp < p_hi) {
+        if (lane == 0) {
             const int tx = tile % ntx, ty = tile / ntx + ty0;   // ty0: first tile row of this launch (row-band split)
             const int rx0 = tx * step_x, ry0 = ty * step_y;
-            if (wp == 0) tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar[g]);
-            else tma_load_2d(&st.pl[wp - 1][0][0], (&maps.dxy) + (wp - 1), rx0, ry0, &full_bar[g]);
+            for (int p = p_lo + (wp + NW - p_lo % NW) % NW; p < p_hi; p += NW) {   // the planes p of the group with p % NW == wp
+                if (p == 0) tma_load_2d(&st.phi[0][0], &maps.phi, rx0 - 4, ry0 - 1, &full_bar[g]);
+                else tma_load_2d(&st.pl[p - 1][0][0], (&maps.dxy) + (p - 1), rx0, ry0, &full_bar[g]);
+            }
         }
     };
     auto issue = [&](int tile) {
