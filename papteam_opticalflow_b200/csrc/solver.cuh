@@ -109,7 +109,12 @@ inline int choose_fused_sweeps(int w, int h, int nsor, int region_h, int forced,
     if (const char* e = getenv("PF_SOR_MODEL")) sscanf(e, "%lf:%lf:%lf:%lf", &ma, &mb, &ml, &mkind);
     double best = 1e300;
     int best_t = 1;
-    for (int t = 1; t <= std::min(nsor, 12); t++) {
+    // 64-px regions shrink by 4 t per pass: t <= 15.  The latency fit may use all of it (a coarse level of <= 148 tiles is one
+    // wave whatever the step, and every pass saved is ~3.5 us: 16.26 -> 15.93 ms per 1920-wide pair with the cap at 15 instead of
+    // 12); the throughput fit never chooses more than 8.
+    int max_fuse = tune == PF_TUNE_LATENCY ? 15 : 12;
+    if (const char* e = getenv("PF_SOR_MAXFUSE")) max_fuse = std::max(1, atoi(e));
+    for (int t = 1; t <= std::min(nsor, max_fuse); t++) {
         SorTiling tx = sor_tiling(w, kSorRegionW, 2 * t), ty = sor_tiling(h, region_h, 2 * t);
         if (tx.ntiles == 0 || ty.ntiles == 0) break;
         const double ctas = (double)tx.ntiles * ty.ntiles;
