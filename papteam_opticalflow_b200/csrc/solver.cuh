@@ -449,6 +449,18 @@ class Plan : public PlanBase {
         try {
             PF_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
             for (auto& ev : ev_) PF_CUDA(cudaEventCreate(&ev));
+            // measured (tools/env_ab.py PF_BRANCHES 0 1): 15.86 -> 15.73 ms for a latency-tuned plan, 19.6 -> 20.0 ms for one
+            // pair alone through a throughput-tuned plan (the cross-stream edges cost what the overlap gains; with 16 pairs
+            // in flight no difference): latency-tuned plans only
+            e = getenv("PF_BRANCHES");
+            branches_ = e ? atoi(e) != 0 : P.tune == PF_TUNE_LATENCY;
+            if (branches_) {
+                PF_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+                for (int i = 0; i < kAux; i++) {
+                    PF_CUDA(cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
+                    PF_CUDA(cudaEventCreateWithFlags(&ev_join_[i], cudaEventDisableTiming));
+                }
+            }
             allocate();
             sor_.init(P.mode, P.device, st_, P.tune);
             set_pdl(P.tune == PF_TUNE_LATENCY);
@@ -470,6 +482,13 @@ class Plan : public PlanBase {
         for (auto& ev : ev_) if (ev) cudaEventDestroy(ev);
         if (ev_block_) cudaEventDestroy(ev_block_);
         ev_block_ = nullptr;
+        if (ev_fork_) cudaEventDestroy(ev_fork_);
+        ev_fork_ = nullptr;
+        for (int i = 0; i < kAux; i++) {
+            if (ev_join_[i]) cudaEventDestroy(ev_join_[i]);
+            if (aux_[i]) cudaStreamDestroy(aux_[i]);
+            ev_join_[i] = nullptr; aux_[i] = nullptr;
+        }
         if (st_) cudaStreamDestroy(st_);
         gexec_ = nullptr; graph_ = nullptr; st_ = nullptr;
         for (auto& gp : gexec_seq_) for (auto& g : gp) g = nullptr;
@@ -747,9 +766,10 @@ class Plan : public PlanBase {
     }
 
     // h then v pass in one kernel (no intermediate plane)
-    void filter_hv(const Img<T>& s, const Img<T>& d, const Taps<T>& th, const Taps<T>& tv) {
+    void filter_hv(const Img<T>& s, const Img<T>& d, const Taps<T>& th, const Taps<T>& tv, cudaStream_t st = nullptr) {
         const dim3 grid(ceil_div(s.w, 64), ceil_div(s.h, 16), s.c);
-#define PF_HV(FH, FV) k_filter_hv_t<T, FH, FV><<<grid, 256, 0, st_>>>(s, d, th, tv)
+        if (!st) st = st_;
+#define PF_HV(FH, FV) k_filter_hv_t<T, FH, FV><<<grid, 256, 0, st>>>(s, d, th, tv)
         switch (th.half * 16 + tv.half) {      // half-widths the pipeline uses get straight-line kernels
             case 0x11: PF_HV(1, 1); break;
             case 0x22: PF_HV(2, 2); break;
@@ -757,7 +777,7 @@ class Plan : public PlanBase {
             case 0x44: PF_HV(4, 4); break;
             case 0x10: PF_HV(1, 0); break;
             case 0x01: PF_HV(0, 1); break;
-            default: k_filter_hv<T><<<grid, 256, 0, st_>>>(s, d, th, tv);
+            default: k_filter_hv<T><<<grid, 256, 0, st>>>(s, d, th, tv);
         }
 #undef PF_HV
         launches_++;
@@ -835,21 +855,42 @@ class Plan : public PlanBase {
     }
 
     // Gaussian pyramid of one frame from its level 0 (S/GaussianPyramid.cpp:79-108)
-    void ph_pyramid(int side) {
+    // `st`: the stream the chain is enqueued on (nullptr = st_); `tmp`: its own blur buffer (the two frames' pyramids run on
+    // two streams side by side, see fork() / join())
+    void ph_pyramid(int side, cudaStream_t st = nullptr, T* tmp = nullptr) {
         auto& pyr = side ? pyr2_ : pyr1_;
+        if (!st) st = st_;
+        if (!tmp) tmp = b_out_;
         for (int i = 1; i < nlev_; i++) {
             const Level& g = geo_[i];
             const Img<T>& src = pyr[g.src];
             Img<T> blurred = src;
             if (g.half > 0) {   // half-width 0 is the identity filter (level 1, quirk Q2)
                 Taps<T> gt = make_taps<T>(g.taps.data(), g.half);
-                blurred = view(b_out_, src.w, src.h, src.c);
-                filter_hv(src, blurred, gt, gt);
+                blurred = view(tmp, src.w, src.h, src.c);
+                filter_hv(src, blurred, gt, gt, st);
             }
-            k_resize<T><<<grid2(g.w, g.h), 128, 0, st_>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
+            k_resize<T><<<grid2(g.w, g.h), 128, 0, st>>>(blurred, pyr[i], g.rate, g.rate, (T)1, 0);
             launches_++;
         }
     }
+
+    // ---- independent kernels of one pair side by side: n auxiliary streams branch off st_ and are joined again.  Inside a
+    //      captured graph these become parallel branches; the arithmetic is untouched.  (PF_BRANCHES=0: one chain.) ----
+    int fork(int n) {
+        if (!branches_) return 0;
+        n = std::min(n, kAux);
+        PF_CUDA(cudaEventRecord(ev_fork_, st_));
+        for (int i = 0; i < n; i++) PF_CUDA(cudaStreamWaitEvent(aux_[i], ev_fork_, 0));
+        return n;
+    }
+    void join(int n) {
+        for (int i = 0; i < n; i++) {
+            PF_CUDA(cudaEventRecord(ev_join_[i], aux_[i]));
+            PF_CUDA(cudaStreamWaitEvent(st_, ev_join_[i], 0));
+        }
+    }
+    cudaStream_t branch(int i, int forked) const { return i < forked ? aux_[i] : st_; }
 
     void ph_lap_init() {
         if (gmix_) {   // S/OpticalFlow.cpp:769-770
@@ -867,11 +908,13 @@ class Plan : public PlanBase {
     void ph_begin() {
         ph_ctx();
         set_phase(PF_T_CONSTRUCTION, 0);
+        const int nb = fork(1);                 // frame 2's import + pyramid next to frame 1's
         k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in1_, pyr1_[0]);
-        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, st_>>>(d_in2_, pyr2_[0]);
+        k_import_hwc<T><<<grid2(P.w, P.h), 128, 0, branch(0, nb)>>>(d_in2_, pyr2_[0]);
         launches_ += 2;
         ph_pyramid(0);
-        ph_pyramid(1);
+        ph_pyramid(1, branch(0, nb), nb ? b_tmp_ : b_out_);
+        join(nb);
         ph_lap_init();
     }
 
@@ -886,15 +929,30 @@ class Plan : public PlanBase {
         c.s1 = view(s1_, w, h, fc_); c.s2 = view(s2_, w, h, fc_); c.tmp = view(tmp_, w, h, fc_);
         c.blend = view(blend_, w, h, fc_); c.imdx = view(imdx_, w, h, fc_);
         c.imdy = view(imdy_, w, h, fc_); c.imdt = view(imdt_, w, h, fc_);
+        // the two feature images and the two flow upsamplings are independent of one another: four branches
+        const int nb = fork(3);
         if (P.c == 1 || P.c == 3) {
             int swap = (k == 0 && P.col_type == 1) ? 1 : 0;
             k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr1_[k], c.f1, c.d5, swap);
-            k_im2feature<T><<<grid2(w, h), 128, 0, st_>>>(pyr2_[k], c.f2, c.d5, swap);
+            k_im2feature<T><<<grid2(w, h), 128, 0, branch(0, nb)>>>(pyr2_[k], c.f2, c.d5, swap);
         } else {
             k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr1_[k], c.f1);
-            k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(pyr2_[k], c.f2);
+            k_copy<T><<<grid2(w, h, fc_), 128, 0, branch(0, nb)>>>(pyr2_[k], c.f2);
         }
         launches_ += 2;
+        if (k != nlev_ - 1) {
+            Img<T> su = view(u_, c.pw, c.ph, 1), sv = view(v_, c.pw, c.ph, 1);
+            Img<T> du = view(u2_, w, h, 1), dv = view(v2_, w, h, 1);
+            double rx = (double)w / c.pw, ry = (double)h / c.ph;
+            T scale = (T)(1 / P.ratio);
+            k_resize<T><<<grid2(w, h), 128, 0, branch(1, nb)>>>(su, du, rx, ry, scale, 1);
+            k_resize<T><<<grid2(w, h), 128, 0, branch(2, nb)>>>(sv, dv, rx, ry, scale, 1);
+            std::swap(u_, u2_);
+            std::swap(v_, v2_);
+            launches_ += 2;
+        }
+        join(nb);
+        const int nb2 = fork(1);               // the smoothed Im1 features (needs f1 only) next to the level-start warp
         if (bicubic_) {
             // warpImageBicubicRef differentiates the image it warps on every call (S/Image.h:2587-2595); the
             // Im2 features are constant within a level, so the three derivative images are computed once
@@ -911,15 +969,6 @@ class Plan : public PlanBase {
             k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(c.f2, c.wf);
             launches_++;
         } else {
-            Img<T> su = view(u_, c.pw, c.ph, 1), sv = view(v_, c.pw, c.ph, 1);
-            Img<T> du = view(u2_, w, h, 1), dv = view(v2_, w, h, 1);
-            double rx = (double)w / c.pw, ry = (double)h / c.ph;
-            T scale = (T)(1 / P.ratio);
-            k_resize<T><<<grid2(w, h), 128, 0, st_>>>(su, du, rx, ry, scale, 1);
-            k_resize<T><<<grid2(w, h), 128, 0, st_>>>(sv, dv, rx, ry, scale, 1);
-            std::swap(u_, u2_);
-            std::swap(v_, v2_);
-            launches_ += 2;
             if (bicubic_) {
                 bicubic_inner(k, 0);   // S/OpticalFlow.cpp:814-815: no threshold() at the level start
             } else {
@@ -930,7 +979,8 @@ class Plan : public PlanBase {
         // Im1 is constant within a level: its smoothed copy is computed once instead of every
         // outer iteration (S/OpticalFlow.cpp:89 recomputes it; same arithmetic, same result)
         set_phase(PF_T_PHASE1_GENERATE, k);
-        filter_hv(c.f1, c.s1, c.g5, c.g5);
+        filter_hv(c.f1, c.s1, c.g5, c.g5, branch(0, nb2));
+        join(nb2);
         if (fused_ && fused_tma_) {
             const int ty = small_tiles(w, h) ? kFTYs : kFTY;
             c.fmaps.wf = make_image_map(c.wf.p, w, h, fc_, c.wf.pitch, c.wf.plane, 72, ty + 8);
@@ -1221,6 +1271,10 @@ class Plan : public PlanBase {
     bool lex_ = false, use_graph_ = true, fused_ = true, fused_tma_ = true, profiling_ = false, open_ = false;
     bool bicubic_ = false, gmix_ = false;   // alternative solver branches
     bool pdl_ = false;
+    static constexpr int kAux = 3;
+    cudaStream_t aux_[kAux] = {nullptr, nullptr, nullptr};   // branches of one pair's launch sequence (fork / join)
+    cudaEvent_t ev_fork_ = nullptr, ev_join_[kAux] = {nullptr, nullptr, nullptr};
+    bool branches_ = true;
     bool fused_cp_ = false;                  // channel-parallel assembly kernel on the small-tile levels (fused_cp.cuh)
     static constexpr int kCpSeg = 2;
     int nlev_ = 0, fc_ = 0;
