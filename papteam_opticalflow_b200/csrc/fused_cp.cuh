@@ -10,6 +10,13 @@
 // right-hand sides, inverse diagonals).  Same arithmetic per pixel as k_fused_tma: the results are bit-identical
 // (tests: every latency-tuned solve against the throughput-tuned one).  Used by latency-tuned plans on the levels whose
 // 64x16 tiling leaves most SMs idle (Plan::small_tiles); more halo work per pixel, which is why nothing else uses it.
+//
+// WARP = true folds the flow update + bilinear warp (k_update_warp, S/OpticalFlow.cpp:513-516 -> S/ImageProcessing.h:483-503)
+// into the head of the kernel: all threads compute the sampling geometry of the 72 x (TY+8) halo tile once (flow u + du of
+// the PREVIOUS solve, k_update_warp's arithmetic) into shared memory, every channel group gathers its channel's warped tile
+// from it (entries outside the image take the nearest in-image pixel's value = the replicate rule), group 0 stores the
+// updated flow of the tile's own pixels to a second pair of planes.  One launch and one dependent chain less per outer
+// iteration (~6 us of ~25 on the coarse levels); the warped features are never written to memory.
 #pragma once
 #include "fused_tma.cuh"
 
@@ -26,13 +33,19 @@ struct alignas(128) FusedCpChannel {
     T out[5][TY][TX];             // psi Ix, psi Iy, Ix, Iy, It of this channel at the centre pixels
 };
 
+struct alignas(16) WarpGeom {     // sampling geometry of one entry of the halo tile
+    int o00, o01, o10, o11;       // offsets inside a feature plane of Im2; o00 < 0: outside the image, -(o00 + 1) = Im1 offset
+    float w00, w01, w10, w11;     // (double in the FP64 instantiation is not needed: the folded form is FP32 only)
+};
+
 template <typename T, int TY>
-inline size_t fused_cp_smem_bytes(int channels) {
+inline size_t fused_cp_smem_bytes(int channels, bool warp = false) {
     typedef FusedCpChannel<T, TY> Ch;
-    return sizeof(Ch) * (size_t)channels + 2 * round_up(sizeof(T) * (TY + 2) * Ch::RW, 128) + sizeof(T) * 65 * (TY + 1) + 128;
+    return sizeof(Ch) * (size_t)channels + 2 * round_up(sizeof(T) * (TY + 2) * Ch::RW, 128) + round_up(sizeof(T) * 65 * (TY + 1), 128) +
+           (warp ? sizeof(WarpGeom) * Ch::RH * Ch::RW : 0) + 128;
 }
 
-template <typename T, int TY, int SEG>
+template <typename T, int TY, int SEG, bool WARP = false>
 __global__ void __launch_bounds__(1024, 1)
 k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     typedef FusedCpChannel<T, TY> Ch;
@@ -53,6 +66,8 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     T* const tu_s = reinterpret_cast<T*>(smem_dyn + sizeof(Ch) * (size_t)C);          // [UH][RW], TMA destination
     T* const tv_s = reinterpret_cast<T*>(smem_dyn + sizeof(Ch) * (size_t)C + kUvBytes);
     T* const tphi = reinterpret_cast<T*>(smem_dyn + sizeof(Ch) * (size_t)C + 2 * kUvBytes);   // [PH][PW]
+    constexpr size_t kPhiBytes = (sizeof(T) * PW * PH + 127) / 128 * 128;
+    WarpGeom* const geom = reinterpret_cast<WarpGeom*>(smem_dyn + sizeof(Ch) * (size_t)C + 2 * kUvBytes + kPhiBytes);   // WARP only
 
     const int W = a.w, H = a.h;
     const int x0 = blockIdx.x * TX, y0 = (blockIdx.y + a.ty0) * TY;
@@ -61,7 +76,7 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     const int gw = lt >> 5;                                    // warp within the group
     const int col = lt & (TX - 1), seg = lt / TX;
     const bool border = x0 < 4 || y0 < 4 || x0 + TX + 4 > W || y0 + TY + 4 > H;
-    const bool uv_staged = a.du == nullptr;
+    const bool uv_staged = !WARP && a.du == nullptr;   // WARP: the tail's flow tiles are u + wdu, built with plain loads
     Ch& ch = chs[g];
 
     if (tid == 0) {
@@ -71,7 +86,7 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     __syncthreads();
     // all input tiles at once: warp k issues copy k (2 per channel, then u and v); thread 0 arms the byte count
     if (tid == 0) {
-        uint32_t bytes = (uint32_t)(sizeof(T) * (RHt * RW + SH * RW)) * (uint32_t)C;
+        uint32_t bytes = (uint32_t)(sizeof(T) * ((WARP ? 0 : RHt * RW) + SH * RW)) * (uint32_t)C;
         if (uv_staged) bytes += (uint32_t)(2 * sizeof(T) * UH * RW);
         mbar_expect_tx(&full_bar, bytes);
     }
@@ -80,7 +95,7 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
             if (k < 2 * C) {
                 const int c = k >> 1;
                 if (k & 1) tma_load_3d(&chs[c].s1[0][0], &maps.s1, x0 - 4, y0 - 2, c, &full_bar);
-                else tma_load_3d(&chs[c].raw[0][0], &maps.wf, x0 - 4, y0 - 4, c, &full_bar);
+                else if (!WARP) tma_load_3d(&chs[c].raw[0][0], &maps.wf, x0 - 4, y0 - 4, c, &full_bar);
             } else if (uv_staged) {
                 if (k == 2 * C) tma_load_2d(tu_s, &maps.u, x0 - 4, y0 - 1, &full_bar);
                 else tma_load_2d(tv_s, &maps.v, x0 - 4, y0 - 1, &full_bar);
@@ -106,13 +121,103 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
     const T d0 = a.d5.v[0], d1 = a.d5.v[1], d3 = a.d5.v[3], d4 = a.d5.v[4];   // centre tap is 0
     const bool active = !(a.lap && a.lap[g] < 1e-20);   // S/OpticalFlow.cpp:399-400
 
-    mbar_wait(&full_bar, 0);
     T* raw = &ch.raw[0][0];
     T* s1t = &ch.s1[0][0];
-    if (border) {
-        fixup(raw, RHt, RW, RW, x0 - 4, y0 - 4, gw, NWG);
-        fixup(s1t, SH, RW, RW, x0 - 4, y0 - 2, gw, NWG);
+    if constexpr (WARP) {
+        // ---- flow update + sampling geometry of every entry of the halo tile, once for all channels (k_update_warp's
+        //      arithmetic); entries outside the image take their nearest in-image pixel (the replicate rule) ----------------
+        constexpr int NE = RHt * RW;
+        // (two entries per thread and trip, their four flow loads issued together: one memory round trip per trip)
+        for (int e0 = tid; e0 < NE; e0 += 2 * blockDim.x) {
+            int ee[2]; size_t of[2]; int Yq[2], Xq[2]; bool own[2]; T uu[2], vv[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                ee[q] = e0 + q * blockDim.x;
+                const int e = min(ee[q], NE - 1);
+                const int ry = e / RW, rx = e - ry * RW;
+                const int Yr = y0 - 4 + ry, Xr = x0 - 4 + rx;
+                Yq[q] = clampi(Yr, H); Xq[q] = clampi(Xr, W);
+                own[q] = Yr == Yq[q] && Xr == Xq[q] && ry >= 4 && ry < 4 + TY && rx >= 4 && rx < 4 + TX;   // the tile's own pixels
+                of[q] = (size_t)Yq[q] * a.pitch + Xq[q];
+                uu[q] = a.u[of[q]]; vv[q] = a.v[of[q]];
+            }
+            if (a.wdu) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) { uu[q] += a.wdu[of[q]]; vv[q] += a.wdv[of[q]]; }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (ee[q] >= NE) continue;
+                if (a.wdu && own[q]) {
+                    a.uo[of[q]] = uu[q];
+                    a.vo[of[q]] = vv[q];
+                }
+                const int X = Xq[q], Y = Yq[q];
+                WarpGeom gm;
+                T fx, fy;
+                const SamplePos px = sample_pos(X, uu[q], W, fx), py = sample_pos(Y, vv[q], H, fy);
+                if (px.out || py.out) {
+                    gm.o00 = -(Y * a.f1.pitch + X) - 1;
+                    gm.o01 = gm.o10 = gm.o11 = 0;
+                    gm.w00 = gm.w01 = gm.w10 = gm.w11 = 0;
+                } else {
+                    const int xa = clampi(px.i, W), xb = clampi(px.i + 1, W), ya = clampi(py.i, H), yb = clampi(py.i + 1, H);
+                    const T ax0 = fabs((T)1 - fx), ax1 = fabs((T)0 - fx), ay0 = fabs((T)1 - fy), ay1 = fabs((T)0 - fy);
+                    gm.w00 = ax0 * ay0; gm.w01 = ax0 * ay1; gm.w10 = ax1 * ay0; gm.w11 = ax1 * ay1;
+                    gm.o00 = ya * a.f2.pitch + xa; gm.o01 = yb * a.f2.pitch + xa;
+                    gm.o10 = ya * a.f2.pitch + xb; gm.o11 = yb * a.f2.pitch + xb;
+                }
+                // (two 16-byte stores: a 32-byte struct store would be split into conflicting 4-byte ones)
+                reinterpret_cast<int4*>(&geom[ee[q]])[0] = make_int4(gm.o00, gm.o01, gm.o10, gm.o11);
+                reinterpret_cast<float4*>(&geom[ee[q]])[1] = make_float4(gm.w00, gm.w01, gm.w10, gm.w11);
+            }
+        }
         __syncthreads();
+        // ---- every group gathers its channel's warped tile ---------------------------------------------------------------
+        {
+            const T* const p2 = a.f2.ch(g);
+            const T* const p1 = a.f1.ch(g);
+            constexpr int EPT = (NE + NT - 1) / NT;
+            T v00[EPT], v01[EPT], v10[EPT], v11[EPT];
+#pragma unroll
+            for (int i = 0; i < EPT; i++) {
+                const int e = lt + i * NT;
+                v00[i] = v01[i] = v10[i] = v11[i] = 0;
+                if (e < NE) {
+                    const int4 o = reinterpret_cast<const int4*>(&geom[e])[0];
+                    if (o.x >= 0) { v00[i] = p2[o.x]; v01[i] = p2[o.y]; v10[i] = p2[o.z]; v11[i] = p2[o.w]; }
+                    else v00[i] = p1[-(o.x + 1)];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < EPT; i++) {
+                const int e = lt + i * NT;
+                if (e < NE) {
+                    const float4 wq = reinterpret_cast<const float4*>(&geom[e])[1];
+                    T acc;
+                    if (geom[e].o00 >= 0) {
+                        acc = 0;
+                        acc += v00[i] * (T)wq.x;
+                        acc += v01[i] * (T)wq.y;
+                        acc += v10[i] * (T)wq.z;
+                        acc += v11[i] * (T)wq.w;
+                    } else {
+                        acc = v00[i];          // Im1 fallback outside the image
+                    }
+                    raw[e] = acc;
+                }
+            }
+        }
+        mbar_wait(&full_bar, 0);
+        if (border) fixup(s1t, SH, RW, RW, x0 - 4, y0 - 2, gw, NWG);
+        __syncthreads();
+    } else {
+        mbar_wait(&full_bar, 0);
+        if (border) {
+            fixup(raw, RHt, RW, RW, x0 - 4, y0 - 4, gw, NWG);
+            fixup(s1t, SH, RW, RW, x0 - 4, y0 - 2, gw, NWG);
+            __syncthreads();
+        }
     }
     // ---- horizontal smoothing (k_fused_tma's stage, one channel per group) ---------------------------------------
     {
@@ -239,7 +344,20 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
             }
         }
     };
-    if (uv_staged) {
+    if (WARP) {
+        // the new flow u + wdu on the tile and its halo (phi AND the Laplacian act on it: it is this iteration's u)
+        for (int uy = warp; uy < UH; uy += nwarp) {
+            const size_t ro = (size_t)clampi(y0 - 1 + uy, H) * a.pitch;
+            for (int ux = lane; ux < UW; ux += 32) {
+                const size_t o = ro + clampi(x0 - 1 + ux, W);
+                T uv = a.u[o], vv = a.v[o];
+                if (a.wdu) { uv += a.wdu[o]; vv += a.wdv[o]; }
+                tu[uy * US + ux] = uv;
+                tv[uy * US + ux] = vv;
+            }
+        }
+        __syncthreads();
+    } else if (uv_staged) {
         if (border) {                                   // replicate clamp over TMA's zero fill
             fixup(tu - 3, UH, RW, RW, x0 - 4, y0 - 1, warp, nwarp);
             fixup(tv - 3, UH, RW, RW, x0 - 4, y0 - 1, warp, nwarp);
@@ -267,7 +385,7 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         }
     }
     __syncthreads();
-    if (!uv_staged) {
+    if (!WARP && !uv_staged) {
         load_uv(false);
         __syncthreads();
     }

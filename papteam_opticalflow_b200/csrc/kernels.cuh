@@ -970,6 +970,12 @@ struct FusedArgs {
     T alpha, omega, eps;
     Taps<T> g5, d5;
     int ty0 = 0;                   // first tile row of this launch (k_fused_tma; a row band of the level, multigpu.cuh)
+    // k_fused_cp<..., WARP = true> only: the warp of S/OpticalFlow.cpp:513-516 is computed inside the assembly kernel from
+    // the level's features f1, f2 and the flow u + wdu, v + wdv (wdu == nullptr: the flow is u, v as they are); the
+    // updated flow of the tile's pixels is stored to uo, vo (u, v stay intact: other CTAs read their halos from them)
+    Img<T> f1, f2;
+    const T *wdu = nullptr, *wdv = nullptr;
+    T *uo = nullptr, *vo = nullptr;
 };
 
 // psi = 1 / (2 sqrt(t + eps)).  FP64 keeps the reference's expression; FP32 uses the hardware

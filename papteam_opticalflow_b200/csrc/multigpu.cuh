@@ -54,6 +54,7 @@ class MultiPlan {
             q.device = devs_[g];
             plans_.emplace_back(new Plan<float>(q));
             plans_.back()->set_pdl(false);      // flag-ordered passes and cross-device edges: ordinary launches only
+            plans_.back()->set_fold(false);     // the phases are driven from here, per band
             cudaEvent_t e1, e2;
             PF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
             PF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));

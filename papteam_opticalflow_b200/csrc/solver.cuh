@@ -441,9 +441,15 @@ class Plan : public PlanBase {
                 // channel-parallel form for the coarse levels of latency-tuned plans (fused_cp.cuh): C groups of 64 * kCpSeg threads
                 e = getenv("PF_FUSED_CP");
                 fused_cp_ = !(e && !atoi(e)) && 64 * kCpSeg * fc_ <= 1024;
-                if (fused_cp_)
+                if (fused_cp_) {
                     PF_CUDA(cudaFuncSetAttribute(k_fused_cp<T, kFTYs, kCpSeg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)fused_cp_smem_bytes<T, kFTYs>(fc_)));
+                    PF_CUDA(cudaFuncSetAttribute(k_fused_cp<T, kFTYs, kCpSeg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)fused_cp_smem_bytes<T, kFTYs>(fc_, true)));
+                    // update + warp folded into that kernel (latency-tuned plans, default solver branches, nInner = 1)
+                    e = getenv("PF_FUSED_WARP");
+                    fold_ = !(e && !atoi(e)) && P.tune == PF_TUNE_LATENCY && P.n_inner == 1 && !bicubic_ && !gmix_ && fused_;
+                }
             }
         }
         try {
@@ -826,6 +832,8 @@ class Plan : public PlanBase {
         T *du_e, *dv_e, *du2_e, *dv2_e, *u_e, *v_e, *u2_e, *v2_e;   // pointer roles on entry
         int pw, ph;                                                   // previous (coarser) level size
         int w, h, pitch;                                              // current level
+        int it = 0;                                                   // outer iteration of the level being enqueued
+        bool folded = false;                                          // this level: update + warp inside the assembly kernel
         Img<T> f1, f2, wf, s1, s2, tmp, blend, imdx, imdy, imdt;
         Img<T> gix, giy, gixy;                                        // Bicubic inner warp: derivative images of f2
         FusedMaps fmaps;
@@ -835,6 +843,7 @@ class Plan : public PlanBase {
   public:
     // programmatic dependent launch of the chain kernels (common.cuh): latency-tuned plans; never the plans of a MultiPlan
     void set_pdl(bool on) { pdl_ = on; sor_.pdl = on; }
+    void set_fold(bool on) { fold_ = fold_ && on; }   // MultiPlan drives the phases itself: never folded there
     int n_outer_at(int k) const { return P.n_outer + k; }
     int n_sor_at(int k) const { return P.n_sor + 3 * k; }
     int level_w(int k) const { return geo_[k].w; }
@@ -952,6 +961,7 @@ class Plan : public PlanBase {
             launches_ += 2;
         }
         join(nb);
+        c.folded = fold_ && fused_tma_ && small_tiles(w, h);
         const int nb2 = fork(1);               // the smoothed Im1 features (needs f1 only) next to the level-start warp
         if (bicubic_) {
             // warpImageBicubicRef differentiates the image it warps on every call (S/Image.h:2587-2595); the
@@ -966,9 +976,11 @@ class Plan : public PlanBase {
         if (k == nlev_ - 1) {
             PF_CUDA(cudaMemsetAsync(u_, 0, plane_bytes, st_));
             PF_CUDA(cudaMemsetAsync(v_, 0, plane_bytes, st_));
-            k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(c.f2, c.wf);
-            launches_++;
-        } else {
+            if (!c.folded) {
+                k_copy<T><<<grid2(w, h, fc_), 128, 0, st_>>>(c.f2, c.wf);
+                launches_++;
+            }
+        } else if (!c.folded) {
             if (bicubic_) {
                 bicubic_inner(k, 0);   // S/OpticalFlow.cpp:814-815: no threshold() at the level start
             } else {
@@ -1026,7 +1038,18 @@ class Plan : public PlanBase {
             fa.alpha = (T)P.alpha; fa.omega = (T)1.8; fa.eps = c.eps;
             fa.g5 = c.g5; fa.d5 = c.d5;
             if (fused_tma_) {
-                if (small_tiles(w, h) && fused_cp_) {
+                if (c.folded) {
+                    if constexpr (!kF64) {
+                        // the flow of this iteration is u + du of the previous solve (none before the first); it lands in u2 / v2
+                        const bool inc = c.it > 0;
+                        fa.f1 = c.f1; fa.f2 = c.f2;
+                        fa.wdu = inc ? du_ : nullptr; fa.wdv = inc ? dv_ : nullptr;
+                        fa.uo = u2_; fa.vo = v2_;
+                        launch_chain(pdl_, k_fused_cp<T, kFTYs, kCpSeg, true>, dim3(ceil_div(w, 64), ceil_div(h, kFTYs)), dim3(64 * kCpSeg * fc_),
+                                     fused_cp_smem_bytes<T, kFTYs>(fc_, true), st_, c.fmaps, fa);
+                        if (inc) { std::swap(u_, u2_); std::swap(v_, v2_); }
+                    }
+                } else if (small_tiles(w, h) && fused_cp_) {
                     if constexpr (!kF64) {
                         fa.ty0 = row_lo / kFTYs;
                         launch_chain(pdl_, k_fused_cp<T, kFTYs, kCpSeg>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), dim3(64 * kCpSeg * fc_),
@@ -1086,6 +1109,14 @@ class Plan : public PlanBase {
     void ph_update(int k, int warp_lo = 0, int warp_hi = 0x7fffffff) {
         Ctx& c = cx_;
         set_phase(PF_T_PHASE6_UPDATE, k);
+        if (c.folded) {
+            // the next assembly updates and warps; after the last iteration of the level only the flow update is left
+            if (c.it + 1 == n_outer_at(k)) {
+                k_add_flow<T><<<grid2(c.w, c.h), 128, 0, st_>>>(u_, v_, du_, dv_, c.w, c.pitch);
+                launches_++;
+            }
+            return;
+        }
         if (bicubic_ || gmix_ || (kF64 && lex_)) { warp_lo = 0; warp_hi = 0x7fffffff; }   // these read the whole warped image
         if (bicubic_) {
             k_add_flow<T><<<grid2(c.w, c.h), 128, 0, st_>>>(u_, v_, du_, dv_, c.w, c.pitch);
@@ -1142,6 +1173,7 @@ class Plan : public PlanBase {
         for (int k = nlev_ - 1; k >= 0; k--) {
             ph_level(k);
             for (int it = 0; it < n_outer_at(k); it++) {
+                cx_.it = it;
                 ph_getdxs(k);
                 for (int hh = 0; hh < P.n_inner; hh++) {
                     ph_assemble(k, hh);
@@ -1275,6 +1307,7 @@ class Plan : public PlanBase {
     cudaStream_t aux_[kAux] = {nullptr, nullptr, nullptr};   // branches of one pair's launch sequence (fork / join)
     cudaEvent_t ev_fork_ = nullptr, ev_join_[kAux] = {nullptr, nullptr, nullptr};
     bool branches_ = true;
+    bool fold_ = false;                      // k_fused_cp<..., WARP>: update + warp inside the assembly of the small-tile levels
     bool fused_cp_ = false;                  // channel-parallel assembly kernel on the small-tile levels (fused_cp.cuh)
     static constexpr int kCpSeg = 2;
     int nlev_ = 0, fc_ = 0;
