@@ -961,7 +961,7 @@ class Plan : public PlanBase {
             launches_ += 2;
         }
         join(nb);
-        c.folded = fold_ && fused_tma_ && small_tiles(w, h);
+        c.folded = fold_ && fused_tma_ && cp_level(w, h);
         const int nb2 = fork(1);               // the smoothed Im1 features (needs f1 only) next to the level-start warp
         if (bicubic_) {
             // warpImageBicubicRef differentiates the image it warps on every call (S/Image.h:2587-2595); the
@@ -1049,7 +1049,7 @@ class Plan : public PlanBase {
                                      fused_cp_smem_bytes<T, kFTYs>(fc_, true), st_, c.fmaps, fa);
                         if (inc) { std::swap(u_, u2_); std::swap(v_, v2_); }
                     }
-                } else if (small_tiles(w, h) && fused_cp_) {
+                } else if (cp_level(w, h)) {
                     if constexpr (!kF64) {
                         fa.ty0 = row_lo / kFTYs;
                         launch_chain(pdl_, k_fused_cp<T, kFTYs, kCpSeg>, dim3(ceil_div(w, 64), ceil_div(row_hi, kFTYs) - fa.ty0), dim3(64 * kCpSeg * fc_),
@@ -1296,6 +1296,9 @@ class Plan : public PlanBase {
 #define PF_FUSED_SEGS 4
 #endif
     static constexpr int kFTYs = kF64 ? 8 : PF_FUSED_TYS, kFSEGs = kF64 ? 8 : PF_FUSED_SEGS;
+    // the channel-parallel kernel holds two CTAs of C x 128 threads per SM: worth it while all its tiles are resident at once
+    // (the 455-px level of the 1920 pyramid has 512 of them: 0.40 ms per level with it, 0.28 ms without)
+    bool cp_level(int w, int h) const { return fused_cp_ && small_tiles(w, h) && ceil_div(w, 64) * ceil_div(h, kFTYs) <= 2 * 148; }
     bool small_tiles(int w, int h) const {
         if (const char* e = getenv("PF_FUSED_SMALL")) return atoi(e) != 0 && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
         return P.tune == PF_TUNE_LATENCY && ceil_div(w, 64) * ceil_div(h, kFTY) <= 148;
