@@ -146,7 +146,13 @@ struct SorRunner {
     bool pdl = false;    // launch the tile kernel with programmatic stream serialisation (common.cuh; latency-tuned plans)
     int lex_from = -1;   // experiment (PF_LEX_FROM=k): pyramid levels >= k use the lexicographic kernel in every mode
     bool lex_band = true;          // k_sor_lex (band-march) instead of the grid-synchronised k_sor_wavefront (PF_LEX_IMPL=coop)
-    static constexpr int kLexNS = 8;
+    // sweeps (= compute warps) per CTA of k_sor_lex.  More sweeps per CTA mean fewer hand-offs between sweep groups (each costs
+    // ~18 steps of latency): FP32 16 (19 warps x 96 registers fill the register file; measured 4 / 8 / 16: 107 / 83 / 71 ms per
+    // 1920-wide pair in fp32_wavefront, 42.8 / 35.3 / 33.8 ms in fp32_hybrid), FP64 8 (158 registers, 175 KB of rings).
+#ifndef PF_LEX_NS
+#define PF_LEX_NS 16
+#endif
+    static constexpr int kLexNS = kF64 ? 8 : PF_LEX_NS;
     static constexpr size_t kLexFlagWords = 1u << 16;
     int* lex_flags = nullptr;      // ticket + abort + progress words of k_sor_lex, zeroed before every launch
     int* lex_err = nullptr;        // sticky error word
