@@ -307,6 +307,30 @@ def test_plan_resident_path_and_batch():
     plan.close()
 
 
+@pytest.mark.parametrize("case", ["rgb240", "rgb480", "gray240", "rgb960_hybrid"])
+def test_latency_tuned_plans_change_no_bit(case):
+    """Latency-tuned plans (what the one-shot entry points draw from the pool) take different kernels on the coarse levels --
+    four-warp single-region SOR, up to 15 fused sweeps per pass, the channel-parallel assembly kernel k_fused_cp with the flow
+    update + warp folded in, parallel graph branches -- and must return the bits of the throughput-tuned plans."""
+    w = int(case[3:6]) if case[:3] == "rgb" else 240
+    a, b = load_frame(w, 1), load_frame(w, 2)
+    mode = "fp32_hybrid" if case.endswith("hybrid") else "fp32_redblack"
+    kw = {}
+    if case.startswith("gray"):
+        a, b = (np.ascontiguousarray(x.mean(axis=2, keepdims=True)) for x in (a, b))
+        kw = dict(colType=1, nSOR=20)
+    outs = []
+    for tuning in ("throughput", "latency"):
+        plan = pyflow.FlowPlan(a.shape[0], a.shape[1], a.shape[2], mode=mode, tuning=tuning, **kw)
+        _, u, v, w2 = plan.execute(a, b)
+        _, u_again, _, _ = plan.execute(a, b)          # graph replay: the pointer roles are restored
+        assert np.array_equal(u, u_again)
+        outs.append((u, v, w2))
+        plan.close()
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
+
+
 def test_config5_4k_gray_sor60_both_modes_vs_reference_golden():
     """BASELINE config 5 on one GPU: synthetic 3840x2160 gray pair (known affine motion), colType=1,
     nSORIterations=60, minWidth=20 -> 18 levels, against a stride-16 subsample of the reference's
