@@ -152,6 +152,10 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
                     a.uo[of[q]] = uu[q];
                     a.vo[of[q]] = vv[q];
                 }
+                {   // the tail's flow tiles (halo 1) are rows 3 .. 3 + UH of this tile: same origin and width as the u / v boxes
+                    const int ry = ee[q] / RW, rx = ee[q] - ry * RW;
+                    if (ry >= 3 && ry < 3 + UH) { tu_s[(ry - 3) * RW + rx] = uu[q]; tv_s[(ry - 3) * RW + rx] = vv[q]; }
+                }
                 const int X = Xq[q], Y = Yq[q];
                 WarpGeom gm;
                 T fx, fy;
@@ -345,18 +349,8 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         }
     };
     if (WARP) {
-        // the new flow u + wdu on the tile and its halo (phi AND the Laplacian act on it: it is this iteration's u)
-        for (int uy = warp; uy < UH; uy += nwarp) {
-            const size_t ro = (size_t)clampi(y0 - 1 + uy, H) * a.pitch;
-            for (int ux = lane; ux < UW; ux += 32) {
-                const size_t o = ro + clampi(x0 - 1 + ux, W);
-                T uv = a.u[o], vv = a.v[o];
-                if (a.wdu) { uv += a.wdu[o]; vv += a.wdv[o]; }
-                tu[uy * US + ux] = uv;
-                tv[uy * US + ux] = vv;
-            }
-        }
-        __syncthreads();
+        // the new flow u + wdu on the tile and its halo (phi AND the Laplacian act on it: it is this iteration's u) was left
+        // in the u / v tile buffers by the geometry pass at the head of the kernel, replicate-clamped already
     } else if (uv_staged) {
         if (border) {                                   // replicate clamp over TMA's zero fill
             fixup(tu - 3, UH, RW, RW, x0 - 4, y0 - 1, warp, nwarp);
@@ -435,7 +429,7 @@ k_fused_cp(const __grid_constant__ FusedMaps maps, FusedArgs<T> a) {
         a.bv[o] = -a_ty - a.alpha * lv;
     }
     };
-    if (uv_staged) tail(tu_s + 3, tv_s + 3, std::integral_constant<int, RW>{});
+    if (WARP || uv_staged) tail(tu_s + 3, tv_s + 3, std::integral_constant<int, RW>{});
     else tail(&chs[0].hs[0][0], &chs[0].hs[0][0] + UW * UH, std::integral_constant<int, UW>{});
 }
 
