@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_sor_rb_tile(SorArgs<T> a, int ns
 // as a PERSISTENT kernel (one CTA per SM, tiles dealt round-robin) whose next tile is staged by TMA
 // while the current one is being swept.
 //
-// Per tile one elected thread issues eight 2-D bulk tensor copies (cp.async.bulk.tensor -> SASS
-// UTMALDG) into a shared-memory stage -- phi as a 72 x (RH+1) box at (rx0-4, ry0-1) so that the
-// weights of the left / upper neighbours outside the region come along, the other seven planes as
-// 64 x RH boxes -- and arms one mbarrier with the byte count.  TMA zero-fills everything outside the
+// Per tile eight 2-D bulk tensor copies (cp.async.bulk.tensor -> SASS UTMALDG), one per warp, fill a
+// shared-memory stage -- phi as a 72 x (RH+1) box at (rx0-4, ry0-1) so that the weights of the
+// left / upper neighbours outside the region come along, the other seven planes as 64 x RH boxes --
+// and thread 0 arms one mbarrier with the byte count.  TMA zero-fills everything outside the
 // plane (negative coordinates, row padding, rows past the image), which is exactly the "phantom
 // pixel" convention of the update.  Threads wait on the mbarrier, pull their 2 x R patch from shared
 // memory into registers with conflict-free 8-byte loads, release the stage with one __syncthreads,
