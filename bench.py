@@ -537,6 +537,11 @@ def run_ours(args):
         lat_plan.upload(*pairs[0])
         lat_plan.solve(2)
         single_ms = lat_plan.solve(5) / 5
+        try:
+            lat_plan.profile()
+            lat_launches = int(lat_plan.profile()[1][0])       # launches of the plan the one-shot entry points replay
+        except Exception:
+            lat_launches = None
         lat_plan.close()
         # ---- per-phase attribution + SOR roofline from one eager, event-instrumented solve ----
         plan.profile()
@@ -633,6 +638,7 @@ def run_ours(args):
             "hybrid": hyb,
             "phases_ms": phases,
             "launches_per_solve": int(cnt[0]),
+            "launches_per_solve_latency_plan": lat_launches,
         }
     if dist is not None:
         dist.barrier()
